@@ -1,0 +1,222 @@
+/* odesat_b200.h — C ABI of the B200-native digital-memcomputing (DMM) ODE integrator.
+ *
+ * Drop-in boundary for ONE hot path of AHartNtkn/odesat: the public functions of the Rust
+ * module `odesat::system` (reference `src/lib.rs:3`, `src/system.rs`).  The reference has no
+ * FFI layer; the entry points below are what a ~100-line `ffi.rs` would bind (see
+ * INTEGRATION.md and odesat_b200/host/ffi.rs).  Every function cites the reference interface it
+ * replaces as `file:line` relative to the reference root.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all buffers are HOST memory owned by the caller unless a
+ *    parameter is documented as a device pointer.  Host state layout is the reference's: one
+ *    contiguous vector per replica, `v[R][N]`, `xs[R][M]`, `xl[R][M]` (R = 1 for single-state
+ *    calls).  Element type is `double` for the unsuffixed / `_f64` functions (the reference
+ *    is f64-only) and `float` for `_f32`.
+ *  - every function returns an odesat_status (0 = ok) and never throws, aborts or exits.
+ *    `odesat_last_error()` returns a thread-local message for the last non-zero status.
+ *  - the reference's `Option<T>` arguments are passed as sentinels: NaN for floating-point
+ *    options, a negative value for `Option<usize>`.
+ *  - handles are not thread-safe; one handle drives the CUDA device that was current when it
+ *    was created.  Calls are synchronous: results are on the host when they return.
+ *  - there is NO CPU fallback.  Without a CUDA device every compute entry point returns
+ *    ODESAT_ECUDA.
+ */
+#ifndef ODESAT_B200_H
+#define ODESAT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ODESAT_B200_ABI_VERSION 1
+
+typedef enum odesat_status {
+    ODESAT_OK = 0,
+    ODESAT_EINVAL = 1,       /* bad argument (the reference would panic / index out of bounds) */
+    ODESAT_ECUDA = 2,        /* CUDA runtime failure or no device                              */
+    ODESAT_ENOMEM = 3,
+    ODESAT_EUNSUPPORTED = 4  /* requested engine cannot run this formula                       */
+} odesat_status;
+
+typedef enum odesat_precision { ODESAT_F64 = 0, ODESAT_F32 = 1 } odesat_precision;
+
+/* Which kernel family integrates a replica batch.
+ *  GATHER: general path — any clause length, any N/M/R; replica-major state [row][replica];
+ *          per-variable gather over the variable→clause transpose, contributions added in the
+ *          reference's order (ascending clause, then literal position) ⇒ bit-identical sums.
+ *  TILE  : throughput path — uniform clause length k<=3.., variables of a replica
+ *          tile resident in shared memory, clauses streamed in conflict-free levels. */
+typedef enum odesat_engine { ODESAT_ENGINE_AUTO = 0, ODESAT_ENGINE_GATHER = 1, ODESAT_ENGINE_TILE = 2 } odesat_engine;
+
+/* Clause schedule of the TILE engine.
+ *  EXACT   : order-preserving levelisation — each variable receives its clause contributions in
+ *            ascending clause index, i.e. the reference's summation order (bit-identical dv).
+ *  BALANCED: equal-size colour classes (fewer barriers); per-variable summation order differs
+ *            from the reference's, results agree to rounding (deterministic run to run). */
+typedef enum odesat_schedule { ODESAT_SCHED_EXACT = 0, ODESAT_SCHED_BALANCED = 1 } odesat_schedule;
+
+typedef enum odesat_mode {
+    ODESAT_MODE_BATCH = 0,   /* main.rs:254-323: independent replicas, each stops at its own flag;
+                                winner = lowest replica whose thresholded state satisfies the CNF */
+    ODESAT_MODE_INTER = 1    /* system.rs:241-359: all replicas step together, stop at the first
+                                step on which any replica flags; winner = lowest flagged index   */
+} odesat_mode;
+
+/* Options of `simulate` / `simulate_inter` (system.rs:156-163, 241-248). */
+typedef struct odesat_params {
+    double tolerance;    /* Option<f64>: NaN → 1e-3            (system.rs:174)                 */
+    double step_size;    /* Option<f64>: NaN → adaptive, dt0 = 0.01 (system.rs:190, 205)       */
+    int64_t steps;       /* Option<usize>: < 0 → unbounded     (system.rs:191, 198)            */
+    double learning_rate;/* Option<f64> zeta: NaN → density rule (system.rs:164-173)           */
+    int32_t precision;   /* odesat_precision of the device arithmetic                           */
+    int32_t engine;      /* odesat_engine                                                       */
+    int32_t schedule;    /* odesat_schedule                                                     */
+    int32_t chunk;       /* Euler steps between early-exit polls; <= 0 → 32                     */
+} odesat_params;
+
+typedef struct odesat_formula odesat_formula;   /* device-resident CSR + variable→clause transpose */
+typedef struct odesat_batch odesat_batch;       /* device-resident replica-major state of R replicas */
+
+const char* odesat_last_error(void);
+int odesat_abi_version(void);
+/* Number of visible CUDA devices (0 when there is none); never fails. */
+int odesat_device_count(void);
+
+/* ---- formula: the boundary type `CNFFormula` (cnf.rs:53-57) flattened ------------------------
+ * `lits[j]` = ±(index+1) over normalised variables 0..varnum-1 (negative = is_negated, cnf.rs:5-9);
+ * clause m owns lits[clause_off[m] .. clause_off[m+1]).  Indices are validated here (the
+ * reference panics on out-of-bounds at system.rs:48). */
+int odesat_formula_create(int64_t varnum, int64_t n_clauses, const int64_t* clause_off,
+                          const int32_t* lits, odesat_formula** out);
+void odesat_formula_destroy(odesat_formula* f);
+int odesat_formula_info(const odesat_formula* f, int64_t* varnum, int64_t* n_clauses,
+                        int64_t* n_literals, int32_t* uniform_k);
+/* zeta chosen by the density rule (system.rs:164-173). */
+int odesat_formula_default_zeta(const odesat_formula* f, double* zeta);
+
+/* ---- single-state mirrors of odesat::system (one replica, host buffers in and out) ---------- */
+
+/* system.rs:362-372 init_short_term_memory(&CNFFormula) -> Array1<f64>; xs0[M]. */
+int odesat_init_short_term_memory(const odesat_formula* f, double* xs0);
+int odesat_init_short_term_memory_f32(const odesat_formula* f, float* xs0);
+
+/* system.rs:25-31 compute_derivatives(&State, &mut State, &CNFFormula, zeta, &mut SlabState) -> bool */
+int odesat_compute_derivatives(const odesat_formula* f, const double* v, const double* xs,
+                               const double* xl, double zeta, double* dv, double* dxs, double* dxl,
+                               int* allsat);
+int odesat_compute_derivatives_f32(const odesat_formula* f, const float* v, const float* xs,
+                                   const float* xl, double zeta, float* dv, float* dxs, float* dxl,
+                                   int* allsat);
+
+/* system.rs:93 update_state(&mut State, &State, dt, clause_nums); clause_nums = formula's M. */
+int odesat_update_state(const odesat_formula* f, double* v, double* xs, double* xl,
+                        const double* dv, const double* dxs, const double* dxl, double dt);
+int odesat_update_state_f32(const odesat_formula* f, float* v, float* xs, float* xl,
+                            const float* dv, const float* dxs, const float* dxl, double dt);
+
+/* system.rs:101 max_error(&State, &State) -> f64 (NaN-ignoring max of |a-b| over v, xs, xl). */
+int odesat_max_error(const odesat_formula* f, const double* av, const double* axs,
+                     const double* axl, const double* bv, const double* bxs, const double* bxl,
+                     double* err);
+int odesat_max_error_f32(const odesat_formula* f, const float* av, const float* axs,
+                         const float* axl, const float* bv, const float* bxs, const float* bxl,
+                         double* err);
+
+/* system.rs:141-148 euler_step_fixed(...) -> bool: state updated in place, *allsat is the
+ * flag of the PRE-update state. */
+int odesat_euler_step_fixed(const odesat_formula* f, double* v, double* xs, double* xl, double dt,
+                            double zeta, int* allsat);
+int odesat_euler_step_fixed_f32(const odesat_formula* f, float* v, float* xs, float* xl, double dt,
+                                double zeta, int* allsat);
+
+/* system.rs:111-119 euler_step(..., tolerance, &mut dt, zeta, ...) -> bool. */
+int odesat_euler_step(const odesat_formula* f, double* v, double* xs, double* xl, double tolerance,
+                      double* dt, double zeta, int* allsat);
+int odesat_euler_step_f32(const odesat_formula* f, float* v, float* xs, float* xl, double tolerance,
+                          double* dt, double zeta, int* allsat);
+
+/* system.rs:156-163 simulate(&mut State, &CNFFormula, tolerance, step_size, steps, learning_rate)
+ * -> Vec<bool>.  State is updated in place; assignment[i] = v[i] > 0 (system.rs:238).
+ * steps_taken = loop iterations executed; *allsat = 1 when the loop ended on the flag;
+ * *final_dt (may be NULL) = the adaptive step size at exit.  `params->precision` selects the
+ * device arithmetic; host buffers are f64 for this entry point and f32 for `_f32`. */
+int odesat_simulate(const odesat_formula* f, double* v, double* xs, double* xl,
+                    const odesat_params* params, uint8_t* assignment, int64_t* steps_taken,
+                    int* allsat, double* final_dt);
+int odesat_simulate_f32(const odesat_formula* f, float* v, float* xs, float* xl,
+                        const odesat_params* params, uint8_t* assignment, int64_t* steps_taken,
+                        int* allsat, double* final_dt);
+
+/* ---- replica batches: `batch` (main.rs:278-308) and `simulate_inter` (system.rs:241-248) ----
+ * One call = upload R host states, integrate on the device with per-replica flags and early
+ * exit, verify every thresholded state exactly (cnf.rs:246-264), return the winner.
+ *  v/xs/xl      : host [R][N] / [R][M] / [R][M] initial states; any of them may be NULL, in
+ *                 which case it is generated on the device (v0 from `seed` with the documented
+ *                 counter-based generator, xs0 by init_short_term_memory, xl0 = 1).
+ *  write_back   : non-zero → final states are copied back into v/xs/xl (the reference mutates
+ *                 its `&mut` states); zero → they are left untouched.
+ *  solved_step  : [R] first step index (0-based) whose pre-update state was all-satisfied, -1 if none
+ *  verified     : [R] 1 when the replica's thresholded final state satisfies the CNF exactly
+ *  winner       : BATCH: lowest verified replica; INTER: lowest replica flagged at the earliest
+ *                 flagged step (system.rs:353); -1 when none (assignment then comes from
+ *                 replica R-1 for BATCH — the last one the reference's loop ran — or 0 for INTER,
+ *                 system.rs:357)
+ *  assignment   : [N] thresholded state of the winner
+ *  steps_run    : outer Euler steps executed by the device loop
+ * Adaptive INTER (shared dt across replicas) is not offered: ODESAT_EUNSUPPORTED. */
+int odesat_simulate_batch(const odesat_formula* f, int64_t R, double* v, double* xs, double* xl,
+                          uint64_t seed, int64_t replica_offset, const odesat_params* params,
+                          int32_t mode, int32_t write_back, int64_t* solved_step,
+                          uint8_t* verified, int64_t* winner, uint8_t* assignment,
+                          int64_t* steps_run);
+int odesat_simulate_batch_f32(const odesat_formula* f, int64_t R, float* v, float* xs, float* xl,
+                              uint64_t seed, int64_t replica_offset, const odesat_params* params,
+                              int32_t mode, int32_t write_back, int64_t* solved_step,
+                              uint8_t* verified, int64_t* winner, uint8_t* assignment,
+                              int64_t* steps_run);
+/* system.rs:241-248 simulate_inter(&mut Vec<State>, ...) -> Vec<bool>: INTER mode of the above
+ * with caller-supplied states, written back. */
+int odesat_simulate_inter(const odesat_formula* f, int64_t R, double* v, double* xs, double* xl,
+                          const odesat_params* params, uint8_t* assignment, int64_t* winner,
+                          int64_t* steps_taken);
+
+/* ---- device-resident batch object (what the calls above are built from; used by the
+ *      multi-GPU host layer and the benchmark to keep state in HBM between calls) ------------- */
+int odesat_batch_create(const odesat_formula* f, int64_t R, int32_t precision, int32_t engine,
+                        int32_t schedule, odesat_batch** out);
+void odesat_batch_destroy(odesat_batch* b);
+/* Engine actually selected (AUTO resolved), launches issued so far, bytes of HBM held. */
+int odesat_batch_info(const odesat_batch* b, int32_t* engine, int64_t* kernel_launches,
+                      int64_t* device_bytes);
+/* main.rs:283-289 on the device: v0[r][i] = 2u-1 with u from SplitMix64(seed, replica_offset+r, i),
+ * xs0 by init_short_term_memory, xl0 = 1; resets flags, step counter and dt (0.01). */
+int odesat_batch_init(odesat_batch* b, uint64_t seed, int64_t replica_offset);
+/* Host [R][N]/[R][M] in the batch's precision (double* or float*); resets flags/step/dt. */
+int odesat_batch_upload(odesat_batch* b, const void* v, const void* xs, const void* xl);
+int odesat_batch_download(odesat_batch* b, void* v, void* xs, void* xl);
+/* n fixed Euler steps (system.rs:141-154) on every replica.  freeze != 0: a replica stops after
+ * the update of its flagged step (simulate's `break`, system.rs:193-195).  *device_ms (may be
+ * NULL) = CUDA-event time of the step loop on the library's stream. */
+int odesat_batch_run_fixed(odesat_batch* b, double dt, double zeta, int64_t n, int32_t freeze,
+                           float* device_ms);
+/* n adaptive steps (system.rs:111-139), per-replica dt; flagged replicas stay untouched. */
+int odesat_batch_run_adaptive(odesat_batch* b, double tolerance, double zeta, int64_t n,
+                              float* device_ms);
+/* solved_step[R] (−1 = not flagged yet); *steps_done = Euler steps issued since init/upload. */
+int odesat_batch_status(odesat_batch* b, int64_t* solved_step, int64_t* steps_done);
+/* min over replicas of (solved_step << 32 | replica) — the early-exit key the multi-GPU layer
+ * all-reduces (MIN); INT64_MAX when no replica has flagged. */
+int odesat_batch_first_solved(odesat_batch* b, int64_t* key);
+/* cnf.rs:246-264 on the device: verified[r] = thresholded state of replica r satisfies the CNF. */
+int odesat_batch_verify(odesat_batch* b, uint8_t* verified);
+/* system.rs:238 for one replica: assignment[i] = v[i] > 0. */
+int odesat_batch_assignment(odesat_batch* b, int64_t replica, uint8_t* assignment);
+/* Current adaptive step size of every replica (f64 copy). */
+int odesat_batch_dt(odesat_batch* b, double* dt);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ODESAT_B200_H */

@@ -1,0 +1,428 @@
+// batch.cuh — device-resident replica batch: owns the state in HBM, drives the kernels.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <limits>
+#include <memory>
+
+#include "formula.hpp"
+#include "kernels_gather.cuh"
+#include "tile_engine.cuh"
+
+namespace odesat {
+
+struct BatchBase {
+    const odesat_formula* f = nullptr;
+    int64_t R = 0, Rp = 0;
+    int precision = ODESAT_F64, engine = ODESAT_ENGINE_GATHER, schedule = ODESAT_SCHED_EXACT;
+    int64_t launches = 0, dev_bytes = 0;
+    int64_t step = 0;   // Euler steps issued since init/upload
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    virtual ~BatchBase() {
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+    virtual void init(uint64_t seed, int64_t replica_offset, bool gen_v, bool gen_xs, bool gen_xl) = 0;
+    virtual void upload(const void* v, const void* xs, const void* xl, bool reset) = 0;
+    virtual void download(void* v, void* xs, void* xl) = 0;
+    virtual void run_fixed(double dt, double zeta, int64_t n, int freeze, float* ms) = 0;
+    virtual void run_adaptive(double tol, double zeta, int64_t n, float* ms) = 0;
+    virtual void status(int64_t* solved, int64_t* steps) = 0;
+    virtual int64_t first_key() = 0;
+    virtual void verify(uint8_t* out) = 0;
+    virtual void assignment(int64_t r, uint8_t* out) = 0;
+    virtual void get_dt(double* out) = 0;
+    virtual void set_dt(const double* in) = 0;
+    // single-state helpers (R == 1 mirrors of odesat::system)
+    virtual void derivatives(double zeta, void* dv, void* dxs, void* dxl, int* allsat) = 0;
+    virtual void update_state_with(const void* dv, const void* dxs, const void* dxl, double dt) = 0;
+    virtual double max_error_vs(const void* bv, const void* bxs, const void* bxl) = 0;
+};
+
+template <typename T> struct StateBuf {
+    DevBuf<T> v, xs, xl;
+    void alloc(int64_t N, int64_t M, int64_t Rp, int64_t* ledger) {
+        v.alloc((size_t)(N * Rp), ledger);
+        xs.alloc((size_t)(M * Rp), ledger);
+        xl.alloc((size_t)(M * Rp), ledger);
+    }
+    bool allocated() const { return v.p != nullptr; }
+};
+
+template <typename T> struct BatchImpl final : BatchBase {
+    using U = typename ErrBits<T>::U;
+    // ---- gather engine state ----
+    StateBuf<T> S[2], H, Fb;
+    int cur = 0;
+    DevBuf<int32_t> solved;
+    DevBuf<uint32_t> unsat;     // ring [3][Rp]
+    DevBuf<U> err;
+    DevBuf<T> dtv;
+    DevBuf<T> staging;
+    DevBuf<uint8_t> small8;
+    DevBuf<unsigned long long> key;
+    DevBuf<double> dscratch;
+    // ---- tile engine state ----
+    std::unique_ptr<TileEngine<T>> tile;
+
+    BatchImpl(const odesat_formula* f_, int64_t R_, int engine_, int schedule_) {
+        f = f_;
+        R = R_;
+        Rp = R >= 32 ? pad32(R) : R;
+        precision = sizeof(T) == 4 ? ODESAT_F32 : ODESAT_F64;
+        schedule = schedule_;
+        ODESAT_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        ODESAT_CUDA(cudaEventCreate(&ev0));
+        ODESAT_CUDA(cudaEventCreate(&ev1));
+        std::string why;
+        const bool tile_ok = TileEngine<T>::supports(*f, R, &why);
+        if (engine_ == ODESAT_ENGINE_TILE && !tile_ok)
+            throw Error(ODESAT_EUNSUPPORTED, "tile engine cannot run this formula: " + why);
+        engine = (engine_ == ODESAT_ENGINE_TILE || (engine_ == ODESAT_ENGINE_AUTO && tile_ok && TileEngine<T>::preferred(*f, R)))
+                     ? ODESAT_ENGINE_TILE : ODESAT_ENGINE_GATHER;
+        const int64_t N = f->N, M = f->M;
+        solved.alloc((size_t)std::max<int64_t>(Rp, 1), &dev_bytes);
+        dtv.alloc((size_t)std::max<int64_t>(Rp, 1), &dev_bytes);
+        key.alloc(1, &dev_bytes);
+        if (engine == ODESAT_ENGINE_TILE) {
+            tile.reset(new TileEngine<T>(*f, R, schedule, stream, &dev_bytes));
+        } else {
+            S[0].alloc(N, M, Rp, &dev_bytes);
+            S[1].alloc(N, M, Rp, &dev_bytes);
+            unsat.alloc((size_t)std::max<int64_t>(3 * Rp, 1), &dev_bytes);
+            err.alloc((size_t)std::max<int64_t>(Rp, 1), &dev_bytes);
+        }
+        reset_control();
+    }
+
+    // -------------------------------------------------------------------------------------
+    void geom(int64_t rows, dim3& grid, dim3& block) const {
+        int bx = 1;
+        while (bx < 256 && bx < R) bx <<= 1;
+        const int by = 256 / bx;
+        block = dim3(bx, by, 1);
+        grid = dim3((unsigned)std::max<int64_t>((rows + by - 1) / by, 1), (unsigned)std::max<int64_t>((R + bx - 1) / bx, 1), 1);
+    }
+
+    void reset_control() {
+        step = 0;
+        cur = 0;
+        ODESAT_CUDA(cudaMemsetAsync(solved.p, 0xFF, solved.bytes(), stream));   // -1
+        if (unsat.p) ODESAT_CUDA(cudaMemsetAsync(unsat.p, 0, unsat.bytes(), stream));
+        if (err.p) ODESAT_CUDA(cudaMemsetAsync(err.p, 0, err.bytes(), stream));
+        std::vector<T> h((size_t)std::max<int64_t>(Rp, 1), T(0.01));             // system.rs:205
+        ODESAT_CUDA(cudaMemcpyAsync(dtv.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+        ODESAT_CUDA(cudaStreamSynchronize(stream));
+        if (tile) tile->reset_control();
+    }
+
+    void ensure_staging() {
+        const size_t need = (size_t)(std::max(f->N, f->M) * std::max<int64_t>(R, 1));
+        if (staging.n < need) staging.alloc(need, &dev_bytes);
+    }
+
+    // host [R][X] → device [X][Rp]
+    void put(const void* host, T* dst, int64_t X) {
+        if (X == 0 || R == 0) return;
+        if (R == 1) {
+            ODESAT_CUDA(cudaMemcpyAsync(dst, host, (size_t)X * sizeof(T), cudaMemcpyHostToDevice, stream));
+            return;
+        }
+        ensure_staging();
+        ODESAT_CUDA(cudaMemcpyAsync(staging.p, host, (size_t)(R * X) * sizeof(T), cudaMemcpyHostToDevice, stream));
+        dim3 g((unsigned)((X + 31) / 32), (unsigned)((R + 31) / 32)), b(32, 8);
+        k_transpose_in<T><<<g, b, 0, stream>>>(staging.p, dst, R, X, Rp);
+        ++launches;
+    }
+    void get(void* host, const T* src, int64_t X) {
+        if (X == 0 || R == 0) return;
+        if (R == 1) {
+            ODESAT_CUDA(cudaMemcpyAsync(host, src, (size_t)X * sizeof(T), cudaMemcpyDeviceToHost, stream));
+            return;
+        }
+        ensure_staging();
+        dim3 g((unsigned)((X + 31) / 32), (unsigned)((R + 31) / 32)), b(32, 8);
+        k_transpose_out<T><<<g, b, 0, stream>>>(src, staging.p, R, X, Rp);
+        ++launches;
+        ODESAT_CUDA(cudaMemcpyAsync(host, staging.p, (size_t)(R * X) * sizeof(T), cudaMemcpyDeviceToHost, stream));
+        ODESAT_CUDA(cudaStreamSynchronize(stream));   // staging is reused by the next get()
+    }
+
+    // Canonical replica-major views of the current state (tile engine converts on demand).
+    StateBuf<T>& canon() {
+        if (tile) {
+            if (!S[0].allocated()) S[0].alloc(f->N, f->M, Rp, &dev_bytes);
+            return S[0];
+        }
+        return S[cur];
+    }
+    void tile_to_canon() { if (tile) { launches += tile->export_state(S[0].v.p, S[0].xs.p, S[0].xl.p, Rp); } }
+    void canon_to_tile() { if (tile) { launches += tile->import_state(S[0].v.p, S[0].xs.p, S[0].xl.p, Rp); } }
+
+    void init(uint64_t seed, int64_t replica_offset, bool gen_v, bool gen_xs, bool gen_xl) override {
+        StateBuf<T>& s = canon();
+        if (tile && !(gen_v && gen_xs && gen_xl)) tile_to_canon();
+        dim3 g, b;
+        geom(f->N + f->M, g, b);
+        if (f->N + f->M > 0 && R > 0) {
+            k_init_state<T><<<g, b, 0, stream>>>(s.v.p, s.xs.p, s.xl.p, f->dev.xs0, f->N, f->M, R, Rp, seed,
+                                                  replica_offset, gen_v, gen_xs, gen_xl);
+            ++launches;
+        }
+        ODESAT_CUDA(cudaGetLastError());
+        canon_to_tile();
+        ODESAT_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    void upload(const void* v, const void* xs, const void* xl, bool reset) override {
+        if (reset) reset_control();
+        StateBuf<T>& s = canon();
+        if (tile && !(v && xs && xl)) tile_to_canon();
+        if (v) put(v, s.v.p, f->N);
+        if (xs) put(xs, s.xs.p, f->M);
+        if (xl) put(xl, s.xl.p, f->M);
+        ODESAT_CUDA(cudaGetLastError());
+        canon_to_tile();
+        ODESAT_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    void download(void* v, void* xs, void* xl) override {
+        tile_to_canon();
+        StateBuf<T>& s = canon();
+        if (v) get(v, s.v.p, f->N);
+        if (xs) get(xs, s.xs.p, f->M);
+        if (xl) get(xl, s.xl.p, f->M);
+        ODESAT_CUDA(cudaGetLastError());
+        ODESAT_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    GatherArgs<T> base_args(double zeta) {
+        GatherArgs<T> a;
+        a.f = f->dev;
+        a.R = R;
+        a.Rp = Rp;
+        a.zeta = (T)zeta;
+        a.xl_max = T(1e4) * T(f->M);
+        a.solved_step = solved.p;
+        a.unsat = unsat.p;
+        a.err = err.p;
+        return a;
+    }
+
+    template <int MODE> void launch_gather(const GatherArgs<T>& a) {
+        if (f->N + f->M == 0 || R == 0) return;
+        dim3 g, b;
+        geom(f->N + f->M, g, b);
+        if (f->K == 3) k_gather<T, 3, MODE><<<g, b, 0, stream>>>(a);
+        else k_gather<T, 0, MODE><<<g, b, 0, stream>>>(a);
+        ++launches;
+    }
+
+    void time_begin(float* ms) { if (ms) ODESAT_CUDA(cudaEventRecord(ev0, stream)); }
+    void time_end(float* ms) {
+        if (ms) {
+            ODESAT_CUDA(cudaEventRecord(ev1, stream));
+            ODESAT_CUDA(cudaEventSynchronize(ev1));
+            ODESAT_CUDA(cudaEventElapsedTime(ms, ev0, ev1));
+        }
+        ODESAT_CUDA(cudaStreamSynchronize(stream));
+        ODESAT_CUDA(cudaGetLastError());
+    }
+
+    void run_fixed(double dt, double zeta, int64_t n, int freeze, float* ms) override {
+        ODESAT_REQUIRE(n >= 0, "negative step count");
+        ODESAT_REQUIRE(step + n < (int64_t(1) << 31) - 4, "step counter overflow");
+        if (tile) {
+            time_begin(ms);
+            launches += tile->run_fixed((T)dt, (T)zeta, n, freeze, solved.p, step);
+            step += n;
+            time_end(ms);
+            return;
+        }
+        time_begin(ms);
+        for (int64_t i = 0; i < n; ++i) {
+            GatherArgs<T> a = base_args(zeta);
+            a.v = S[cur].v.p; a.xs = S[cur].xs.p; a.xl = S[cur].xl.p;
+            a.ov = S[1 - cur].v.p; a.oxs = S[1 - cur].xs.p; a.oxl = S[1 - cur].xl.p;
+            a.dt = (T)dt;
+            a.step = (int32_t)step;
+            a.freeze = freeze;
+            launch_gather<G_FIXED>(a);
+            cur = 1 - cur;
+            ++step;
+        }
+        if (n > 0 && R > 0) {
+            k_fold_flags<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(solved.p, unsat.p, R, Rp, (int32_t)(step - 1));
+            ++launches;
+        }
+        time_end(ms);
+    }
+
+    void run_adaptive(double tol, double zeta, int64_t n, float* ms) override {
+        ODESAT_REQUIRE(n >= 0, "negative step count");
+        ODESAT_REQUIRE(step + n < (int64_t(1) << 31) - 4, "step counter overflow");
+        if (tile) throw Error(ODESAT_EUNSUPPORTED, "the tile engine integrates fixed steps only; use the gather engine for adaptive steps");
+        if (!H.allocated()) { H.alloc(f->N, f->M, Rp, &dev_bytes); Fb.alloc(f->N, f->M, Rp, &dev_bytes); }
+        time_begin(ms);
+        for (int64_t i = 0; i < n; ++i) {
+            GatherArgs<T> a = base_args(zeta);
+            a.dt_arr = dtv.p;
+            a.step = (int32_t)step;
+            // pass A: k1 on y → y_half (H), y_full (F), flags
+            a.v = S[cur].v.p; a.xs = S[cur].xs.p; a.xl = S[cur].xl.p;
+            a.ov = H.v.p; a.oxs = H.xs.p; a.oxl = H.xl.p;
+            a.fv = Fb.v.p; a.fxs = Fb.xs.p; a.fxl = Fb.xl.p;
+            launch_gather<G_ADAPT_A>(a);
+            // pass B: k2 on y_half → y_new, error norm
+            a.yv = S[cur].v.p; a.yxs = S[cur].xs.p; a.yxl = S[cur].xl.p;
+            a.v = H.v.p; a.xs = H.xs.p; a.xl = H.xl.p;
+            a.ov = S[1 - cur].v.p; a.oxs = S[1 - cur].xs.p; a.oxl = S[1 - cur].xl.p;
+            launch_gather<G_ADAPT_B>(a);
+            if (R > 0) {
+                k_adapt_c<T><<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(solved.p, unsat.p, err.p, dtv.p, (T)tol, R, (int32_t)step);
+                ++launches;
+            }
+            cur = 1 - cur;
+            ++step;
+        }
+        time_end(ms);
+    }
+
+    void status(int64_t* out, int64_t* steps) override {
+        if (out && R > 0) {
+            std::vector<int32_t> h((size_t)R);
+            ODESAT_CUDA(cudaMemcpyAsync(h.data(), solved.p, (size_t)R * 4, cudaMemcpyDeviceToHost, stream));
+            ODESAT_CUDA(cudaStreamSynchronize(stream));
+            for (int64_t r = 0; r < R; ++r) out[r] = h[r];
+        }
+        if (steps) *steps = step;
+    }
+
+    int64_t first_key() override {
+        const unsigned long long init = (unsigned long long)std::numeric_limits<int64_t>::max();
+        ODESAT_CUDA(cudaMemcpyAsync(key.p, &init, 8, cudaMemcpyHostToDevice, stream));
+        if (R > 0) {
+            k_first_key<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(solved.p, R, 0, key.p);
+            ++launches;
+        }
+        unsigned long long h = 0;
+        ODESAT_CUDA(cudaMemcpyAsync(&h, key.p, 8, cudaMemcpyDeviceToHost, stream));
+        ODESAT_CUDA(cudaStreamSynchronize(stream));
+        return (int64_t)h;
+    }
+
+    void verify(uint8_t* out) override {
+        if (R == 0) return;
+        tile_to_canon();
+        StateBuf<T>& s = canon();
+        DevBuf<uint32_t> bad;
+        bad.alloc((size_t)R);
+        ODESAT_CUDA(cudaMemsetAsync(bad.p, 0, bad.bytes(), stream));
+        if (f->M > 0) {
+            dim3 g, b;
+            geom(f->M, g, b);
+            k_verify<T><<<g, b, 0, stream>>>(f->dev, s.v.p, R, Rp, bad.p);
+            ++launches;
+        }
+        std::vector<uint32_t> h((size_t)R);
+        ODESAT_CUDA(cudaMemcpyAsync(h.data(), bad.p, (size_t)R * 4, cudaMemcpyDeviceToHost, stream));
+        ODESAT_CUDA(cudaStreamSynchronize(stream));
+        ODESAT_CUDA(cudaGetLastError());
+        for (int64_t r = 0; r < R; ++r) out[r] = h[r] ? 0 : 1;
+    }
+
+    void assignment(int64_t r, uint8_t* out) override {
+        ODESAT_REQUIRE(r >= 0 && r < R, "replica index out of range");
+        if (f->N == 0) return;
+        tile_to_canon();
+        StateBuf<T>& s = canon();
+        if (small8.n < (size_t)f->N) small8.alloc((size_t)f->N, &dev_bytes);
+        k_assignment<T><<<(unsigned)((f->N + 255) / 256), 256, 0, stream>>>(s.v.p, f->N, Rp, r, small8.p);
+        ++launches;
+        ODESAT_CUDA(cudaMemcpyAsync(out, small8.p, (size_t)f->N, cudaMemcpyDeviceToHost, stream));
+        ODESAT_CUDA(cudaStreamSynchronize(stream));
+        ODESAT_CUDA(cudaGetLastError());
+    }
+
+    void get_dt(double* out) override {
+        std::vector<T> h((size_t)std::max<int64_t>(R, 1));
+        ODESAT_CUDA(cudaMemcpyAsync(h.data(), dtv.p, (size_t)R * sizeof(T), cudaMemcpyDeviceToHost, stream));
+        ODESAT_CUDA(cudaStreamSynchronize(stream));
+        for (int64_t r = 0; r < R; ++r) out[r] = (double)h[r];
+    }
+    void set_dt(const double* in) override {
+        std::vector<T> h((size_t)std::max<int64_t>(R, 1));
+        for (int64_t r = 0; r < R; ++r) h[r] = (T)in[r];
+        ODESAT_CUDA(cudaMemcpyAsync(dtv.p, h.data(), (size_t)R * sizeof(T), cudaMemcpyHostToDevice, stream));
+        ODESAT_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    // ---- single-state helpers (gather engine only) ---------------------------------------
+    void derivatives(double zeta, void* dv, void* dxs, void* dxl, int* allsat) override {
+        ODESAT_REQUIRE(!tile, "derivatives() needs the gather engine");
+        ODESAT_CUDA(cudaMemsetAsync(unsat.p, 0, unsat.bytes(), stream));
+        GatherArgs<T> a = base_args(zeta);
+        a.v = S[cur].v.p; a.xs = S[cur].xs.p; a.xl = S[cur].xl.p;
+        a.ov = S[1 - cur].v.p; a.oxs = S[1 - cur].xs.p; a.oxl = S[1 - cur].xl.p;
+        launch_gather<G_DERIV>(a);
+        if (dv) get(dv, S[1 - cur].v.p, f->N);
+        if (dxs) get(dxs, S[1 - cur].xs.p, f->M);
+        if (dxl) get(dxl, S[1 - cur].xl.p, f->M);
+        std::vector<uint32_t> h((size_t)std::max<int64_t>(R, 1), 0);
+        ODESAT_CUDA(cudaMemcpyAsync(h.data(), unsat.p, (size_t)R * 4, cudaMemcpyDeviceToHost, stream));
+        ODESAT_CUDA(cudaStreamSynchronize(stream));
+        ODESAT_CUDA(cudaGetLastError());
+        if (allsat) for (int64_t r = 0; r < R; ++r) allsat[r] = h[r] ? 0 : 1;
+        ODESAT_CUDA(cudaMemsetAsync(unsat.p, 0, unsat.bytes(), stream));
+    }
+
+    void update_state_with(const void* dv, const void* dxs, const void* dxl, double dt) override {
+        ODESAT_REQUIRE(!tile, "update_state needs the gather engine");
+        StateBuf<T>& d = S[1 - cur];
+        put(dv, d.v.p, f->N);
+        put(dxs, d.xs.p, f->M);
+        put(dxl, d.xl.p, f->M);
+        if (f->N + f->M > 0 && R > 0) {
+            dim3 g, b;
+            geom(f->N + f->M, g, b);
+            k_update_state<T><<<g, b, 0, stream>>>(S[cur].v.p, S[cur].xs.p, S[cur].xl.p, d.v.p, d.xs.p, d.xl.p, (T)dt,
+                                                    f->N, f->M, R, Rp, T(1e4) * T(f->M));
+            ++launches;
+        }
+        ODESAT_CUDA(cudaStreamSynchronize(stream));
+        ODESAT_CUDA(cudaGetLastError());
+    }
+
+    double max_error_vs(const void* bv, const void* bxs, const void* bxl) override {
+        ODESAT_REQUIRE(!tile && R == 1, "max_error is a single-state call");
+        StateBuf<T>& d = S[1 - cur];
+        put(bv, d.v.p, f->N);
+        put(bxs, d.xs.p, f->M);
+        put(bxl, d.xl.p, f->M);
+        ODESAT_CUDA(cudaMemsetAsync(err.p, 0, err.bytes(), stream));
+        if (f->N + f->M > 0) {
+            dim3 g, b;
+            geom(f->N + f->M, g, b);
+            k_max_error<T><<<g, b, 0, stream>>>(S[cur].v.p, S[cur].xs.p, S[cur].xl.p, d.v.p, d.xs.p, d.xl.p, f->N, f->M,
+                                                 R, Rp, err.p);
+            ++launches;
+        }
+        if (dscratch.n < 1) dscratch.alloc(1, &dev_bytes);
+        k_err_decode<T><<<1, 32, 0, stream>>>(err.p, dscratch.p, 1);
+        ++launches;
+        double h = 0;
+        ODESAT_CUDA(cudaMemcpyAsync(&h, dscratch.p, 8, cudaMemcpyDeviceToHost, stream));
+        ODESAT_CUDA(cudaMemsetAsync(err.p, 0, err.bytes(), stream));
+        ODESAT_CUDA(cudaStreamSynchronize(stream));
+        ODESAT_CUDA(cudaGetLastError());
+        return h;
+    }
+};
+
+}  // namespace odesat
+
+struct odesat_batch {
+    std::unique_ptr<odesat::BatchBase> impl;
+};
