@@ -134,7 +134,8 @@ void simulate_impl(const odesat_formula* f, TH* v, TH* xs, TH* xl, const odesat_
                    int64_t* steps_taken, int* allsat, double* final_dt) {
     ODESAT_REQUIRE(f && v && xs && xl, "NULL state or formula");
     const Resolved r = resolve(f, p);
-    std::unique_ptr<BatchBase> b(make_batch(f, 1, p->precision, p->engine, p->schedule));
+    const int eng = (!r.fixed && p->engine == ODESAT_ENGINE_AUTO) ? ODESAT_ENGINE_GATHER : p->engine;
+    std::unique_ptr<BatchBase> b(make_batch(f, 1, p->precision, eng, p->schedule));
     upload_host<TH>(*b, v, xs, xl, true);
     std::vector<int64_t> solved;
     drive(*b, r, ODESAT_MODE_BATCH, solved);
@@ -157,10 +158,12 @@ void simulate_batch_impl(const odesat_formula* f, int64_t R, TH* v, TH* xs, TH* 
         throw Error(ODESAT_EUNSUPPORTED, "adaptive `inter` shares one dt across replicas in the reference "
                                          "(system.rs:314); only fixed-step inter is offered");
     if (mode == ODESAT_MODE_BATCH) ODESAT_REQUIRE(r.steps >= 0, "batch needs a step count (main.rs:96-97)");
-    std::unique_ptr<BatchBase> b(make_batch(f, R, p->precision, p->engine, p->schedule));
+    // the tile engine integrates fixed steps only: adaptive runs resolve AUTO to the gather engine
+    const int eng = (!r.fixed && p->engine == ODESAT_ENGINE_AUTO) ? ODESAT_ENGINE_GATHER : p->engine;
+    std::unique_ptr<BatchBase> b(make_batch(f, R, p->precision, eng, p->schedule));
     const int64_t NONE = std::numeric_limits<int64_t>::max();
     if (!(v && xs && xl)) b->init(seed, replica_offset, true, true, true);       // main.rs:283-289
-    upload_host<TH>(*b, v, xs, xl, !(v && xs && xl) ? false : true);
+    if (v || xs || xl) upload_host<TH>(*b, v, xs, xl, (v && xs && xl));
     std::vector<int64_t> solved;
     const int64_t key = drive(*b, r, mode, solved);
     std::vector<uint8_t> ver((size_t)std::max<int64_t>(R, 1), 0);

@@ -1,0 +1,209 @@
+// tile_schedule.hpp — host-side "schedule compiler" of the TILE engine.
+//
+// The tile kernel keeps {v, dv} of a replica tile in shared memory and lets one thread per
+// clause add its contributions into dv with a plain read-modify-write.  That is race-free iff
+// the clauses processed between two block barriers touch pairwise distinct variables, so the
+// formula is compiled once, on the host, into LEVELS (colour classes of the clause-conflict
+// graph):
+//   EXACT    level(m) = 1 + max over m's variables of the level of the previous clause that
+//            contains the variable.  Every variable then meets its clauses in ascending
+//            clause index as the levels advance — the order in which the reference's
+//            sequential loop executes `dy.v[i] += …` (system.rs:35-80) — so the running sum
+//            is bit-identical to the reference's.
+//   BALANCED greedy least-loaded colouring into equal-size classes (fewer barriers, no
+//            ordering guarantee; results agree to rounding and are run-to-run deterministic).
+// Inside a level the clause order is free; it is chosen so that the 8 lanes of a quarter-warp
+// (one 128-byte shared-memory wavefront of 16-byte rows) hit 8 distinct bank groups wherever
+// possible, and literal positions inside a clause are permuted for the same purpose (the
+// per-clause arithmetic is symmetric in the literals when the variables are distinct).
+#pragma once
+#include <algorithm>
+#include <array>
+#include <cstdint>
+#include <numeric>
+#include <vector>
+
+#include "formula.hpp"
+
+namespace odesat {
+
+struct TileSchedule {
+    int kind = 0;
+    int64_t M = 0, Mpad = 0;           // real clauses, padded slots (multiple of 32)
+    int nlev = 0;
+    std::vector<int32_t> goff;         // [nlev+1] level boundaries in groups of 32 slots
+    std::vector<int32_t> perm;         // [Mpad] slot → clause index, −1 = padding
+    std::vector<uint64_t> entry;       // [Mpad] packed clause: 3×16-bit row + sign bits + valid
+    double conflict_wavefronts = 0;    // avg shared-memory wavefronts per quarter-warp access (1 = ideal)
+    DevBuf<int32_t> d_goff, d_perm;
+    DevBuf<uint64_t> d_entry;
+};
+
+constexpr uint64_t TILE_VALID_BIT = 1ull << 51;
+
+inline uint64_t pack_entry3(const int32_t* var, const bool* neg) {
+    uint64_t e = TILE_VALID_BIT;
+    for (int j = 0; j < 3; ++j) {
+        e |= (uint64_t)(uint16_t)var[j] << (16 * j);
+        if (neg[j]) e |= 1ull << (48 + j);
+    }
+    return e;
+}
+
+// Arrange the clauses of one level into slots, 8 per quarter-warp, minimising bank-group
+// conflicts (row index mod 8) per literal position.  Greedy: fill each octet from the pool,
+// trying the 6 literal permutations of each candidate; leftovers go in as they are.
+inline void pack_level(const odesat_formula& f, const std::vector<int32_t>& clauses, std::vector<int32_t>& out_perm,
+                       std::vector<uint64_t>& out_entry, double& wavefront_sum, int64_t& wavefront_cnt) {
+    static const int P[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+    const size_t n = clauses.size();
+    std::vector<uint8_t> used(n, 0);
+    size_t remaining = n, scan_from = 0;
+    while (remaining > 0) {
+        // one octet
+        uint8_t mask[3] = {0, 0, 0};   // bank groups taken per literal position
+        int filled = 0;
+        int cnt[3][8] = {};
+        const size_t window = 512;     // bounded look-ahead keeps this O(M · window)
+        size_t looked = 0;
+        while (scan_from < n && used[scan_from]) ++scan_from;
+        for (size_t i = scan_from; i < n && filled < 8 && looked < window; ++i) {
+            if (used[i]) continue;
+            ++looked;
+            const int m = clauses[i];
+            int32_t var[3];
+            bool neg[3];
+            for (int j = 0; j < 3; ++j) {
+                const int32_t l = f.h_lits[f.h_off[m] + j];
+                var[j] = (l < 0 ? -l : l) - 1;
+                neg[j] = l < 0;
+            }
+            for (int p = 0; p < 6; ++p) {
+                const int b0 = var[P[p][0]] & 7, b1 = var[P[p][1]] & 7, b2 = var[P[p][2]] & 7;
+                if (!((mask[0] >> b0) & 1) && !((mask[1] >> b1) & 1) && !((mask[2] >> b2) & 1)) {
+                    mask[0] |= 1 << b0; mask[1] |= 1 << b1; mask[2] |= 1 << b2;
+                    cnt[0][b0]++; cnt[1][b1]++; cnt[2][b2]++;
+                    int32_t pv[3] = {var[P[p][0]], var[P[p][1]], var[P[p][2]]};
+                    bool pn[3] = {neg[P[p][0]], neg[P[p][1]], neg[P[p][2]]};
+                    out_perm.push_back(m);
+                    out_entry.push_back(pack_entry3(pv, pn));
+                    used[i] = 1;
+                    --remaining;
+                    ++filled;
+                    break;
+                }
+            }
+        }
+        // top the octet up with whatever is left (conflicts accepted)
+        for (size_t i = scan_from; i < n && filled < 8 && remaining > 0; ++i) {
+            if (used[i]) continue;
+            const int m = clauses[i];
+            int32_t var[3];
+            bool neg[3];
+            for (int j = 0; j < 3; ++j) {
+                const int32_t l = f.h_lits[f.h_off[m] + j];
+                var[j] = (l < 0 ? -l : l) - 1;
+                neg[j] = l < 0;
+                cnt[j][var[j] & 7]++;
+            }
+            out_perm.push_back(m);
+            out_entry.push_back(pack_entry3(var, neg));
+            used[i] = 1;
+            --remaining;
+            ++filled;
+        }
+        for (int j = 0; j < 3; ++j) {
+            int mx = 0;
+            for (int b = 0; b < 8; ++b) mx = std::max(mx, cnt[j][b]);
+            wavefront_sum += mx;
+            ++wavefront_cnt;
+        }
+        // pad a partial octet only at the very end of the level (caller pads to 32)
+        if (remaining == 0) break;
+    }
+}
+
+inline std::shared_ptr<TileSchedule> build_tile_schedule(const odesat_formula& f, int kind) {
+    auto s = std::make_shared<TileSchedule>();
+    s->kind = kind;
+    s->M = f.M;
+    const int64_t M = f.M, N = f.N;
+    std::vector<int32_t> level(M, 0);
+    int nlev = 0;
+    auto var_of = [&](int64_t m, int j) {
+        const int32_t l = f.h_lits[f.h_off[m] + j];
+        return (l < 0 ? -l : l) - 1;
+    };
+    if (kind == ODESAT_SCHED_EXACT) {
+        std::vector<int32_t> last(N, -1);
+        for (int64_t m = 0; m < M; ++m) {
+            int lv = 0;
+            for (int j = 0; j < 3; ++j) lv = std::max(lv, last[var_of(m, j)] + 1);
+            level[m] = lv;
+            for (int j = 0; j < 3; ++j) last[var_of(m, j)] = lv;
+            nlev = std::max(nlev, lv + 1);
+        }
+    } else {
+        // target: levels of ~1024 clauses, but never fewer colours than the max variable degree
+        int C = (int)std::max<int64_t>(f.max_degree + 2, (M + 1023) / 1024);
+        std::vector<std::vector<uint64_t>> usedc;   // per variable: bitset of colours taken
+        int words = (C + 63 + 64) / 64;             // slack for overflow colours
+        std::vector<uint64_t> bits((size_t)N * words, 0);
+        std::vector<int32_t> load((size_t)words * 64, 0);
+        std::vector<int32_t> order(M);
+        std::iota(order.begin(), order.end(), 0);
+        // most constrained first: clauses whose variables have the highest degree
+        std::vector<int32_t> deg(N);
+        for (int64_t i = 0; i < N; ++i) deg[i] = f.h_voff[i + 1] - f.h_voff[i];
+        std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+            const int da = deg[var_of(a, 0)] + deg[var_of(a, 1)] + deg[var_of(a, 2)];
+            const int db = deg[var_of(b, 0)] + deg[var_of(b, 1)] + deg[var_of(b, 2)];
+            return da > db;
+        });
+        int ncol = C;
+        for (int32_t m : order) {
+            const uint64_t* b0 = &bits[(size_t)var_of(m, 0) * words];
+            const uint64_t* b1 = &bits[(size_t)var_of(m, 1) * words];
+            const uint64_t* b2 = &bits[(size_t)var_of(m, 2) * words];
+            int best = -1, bl = INT32_MAX;
+            for (int c = 0; c < ncol; ++c) {
+                const uint64_t forb = b0[c >> 6] | b1[c >> 6] | b2[c >> 6];
+                if (!((forb >> (c & 63)) & 1) && load[c] < bl) { best = c; bl = load[c]; }
+            }
+            if (best < 0) {
+                if (ncol >= words * 64) throw Error(ODESAT_EINVAL, "balanced schedule ran out of colours");
+                best = ncol++;
+            }
+            level[m] = best;
+            load[best]++;
+            for (int j = 0; j < 3; ++j) bits[(size_t)var_of(m, j) * words + (best >> 6)] |= 1ull << (best & 63);
+        }
+        nlev = ncol;
+    }
+    // bucket by level (stable in clause index), pack each level, pad to whole groups of 32
+    std::vector<std::vector<int32_t>> bucket(nlev);
+    for (int64_t m = 0; m < M; ++m) bucket[level[m]].push_back((int32_t)m);
+    s->goff.assign(1, 0);
+    double wsum = 0;
+    int64_t wcnt = 0;
+    for (int lv = 0; lv < nlev; ++lv) {
+        if (bucket[lv].empty()) continue;
+        pack_level(f, bucket[lv], s->perm, s->entry, wsum, wcnt);
+        while (s->perm.size() % 32) { s->perm.push_back(-1); s->entry.push_back(0); }
+        s->goff.push_back((int32_t)(s->perm.size() / 32));
+    }
+    s->nlev = (int)s->goff.size() - 1;
+    s->Mpad = (int64_t)s->perm.size();
+    s->conflict_wavefronts = wcnt ? wsum / wcnt : 1.0;
+    s->d_goff.alloc(s->goff.size());
+    s->d_perm.alloc(std::max<size_t>(s->perm.size(), 1));
+    s->d_entry.alloc(std::max<size_t>(s->entry.size(), 1));
+    ODESAT_CUDA(cudaMemcpy(s->d_goff.p, s->goff.data(), s->goff.size() * 4, cudaMemcpyHostToDevice));
+    if (!s->perm.empty()) {
+        ODESAT_CUDA(cudaMemcpy(s->d_perm.p, s->perm.data(), s->perm.size() * 4, cudaMemcpyHostToDevice));
+        ODESAT_CUDA(cudaMemcpy(s->d_entry.p, s->entry.data(), s->entry.size() * 8, cudaMemcpyHostToDevice));
+    }
+    return s;
+}
+
+}  // namespace odesat

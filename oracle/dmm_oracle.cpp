@@ -41,8 +41,9 @@ template <typename T> struct K {
 };
 
 // Rust f64::max / f64::min ignore a NaN operand — the same contract as C fmax/fmin.
-template <typename T> inline T rmax(T a, T b) { return std::fmax(a, b); }
-template <typename T> inline T rmin(T a, T b) { return std::fmin(a, b); }
+// Written out (no libm call): NaN in one operand returns the other one.
+template <typename T> inline T rmax(T a, T b) { return (b != b) ? a : ((a != a) ? b : (a > b ? a : b)); }
+template <typename T> inline T rmin(T a, T b) { return (b != b) ? a : ((a != a) ? b : (a < b ? a : b)); }
 
 // system.rs:25-91 compute_derivatives
 template <typename T>
