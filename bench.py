@@ -229,6 +229,16 @@ def run_gpu(args):
     flagged = int((st >= 0).sum())
     b.close()
 
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "engine": eng_name, "schedule": args.schedule, "ms_per_step": ms_max / args.steps,
+                              "value": value, "frac": achieved / peak, "frac_of_8TBs": achieved / 8000.0,
+                              "launches": n_launch, "env": {k: v for k, v in os.environ.items() if k.startswith("ODESAT_")}}))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
     # ---- end to end through the C ABI with HOST (pinned) buffers ------------------------------
     dt_t = torch.float32 if prec == L.F32 else torch.float64
     hv = torch.empty((R, f.varnum), dtype=dt_t).pin_memory()
@@ -307,6 +317,7 @@ def main():
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--engine", default="auto", choices=["auto", "gather", "tile"])
     ap.add_argument("--schedule", default="exact", choices=["exact", "balanced"])
+    ap.add_argument("--quick", action="store_true", help="tuning aid: device-resident timing only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     import __graft_entry__ as g

@@ -14,6 +14,7 @@
 namespace odesat {
 
 struct TileSchedule;   // tile_schedule.hpp
+struct TileLevels;
 
 }  // namespace odesat
 
@@ -30,7 +31,9 @@ struct odesat_formula {
     odesat::DevBuf<int32_t> d_coff, d_lits, d_voff, d_occ_clause, d_occ_slot;
     odesat::DevBuf<int8_t> d_xs0;
     odesat::FormulaDev dev;
-    // tile-engine schedules, built on first use, keyed by (schedule kind, replicas per tile)
+    // tile-engine schedules, built on first use: levels keyed by schedule kind, padded
+    // schedules keyed by kind * 4096 + warps per CTA
+    mutable std::map<int, std::shared_ptr<odesat::TileLevels>> tile_levels;
     mutable std::map<int, std::shared_ptr<odesat::TileSchedule>> tile_sched;
 
     double default_zeta() const {   // system.rs:164-173

@@ -17,6 +17,7 @@
 //   vt  [tiles][N][W]            variables, tile layout
 //   mem [tiles][Mpad][2W]        {xs[W], xl[W]} per clause SLOT (schedule order, padded)
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <string>
@@ -41,9 +42,9 @@ template <> struct TileTraits<double> {
 
 template <typename T> struct TileArgs {
     int64_t N = 0, Mpad = 0, R = 0;
-    int nlev = 0;
-    const int32_t* goff = nullptr;
-    const uint64_t* entry = nullptr;
+    int n_items = 0;
+    const uint32_t* items = nullptr;   // [n_items] packed (base, nvalid, last-of-level)
+    const uint64_t* entry = nullptr;   // [Mpad] packed clauses
     T* vt = nullptr;
     typename TileTraits<T>::Mem* mem = nullptr;
     int32_t* solved = nullptr;
@@ -68,11 +69,99 @@ template <> struct RowIO<double, 1> {
     __device__ static double2 pack_mem(const double* xs, const double* xl) { return make_double2(xs[0], xl[0]); }
 };
 
-// RTERM: evaluate the rigidity term of system.rs:73-80 literally.  It is identically ±0 —
-// and adding it is a bit-exact no-op — whenever every v lies in [-1, 1] and zeta is finite
-// (SURVEY quirk Q1), which holds from the first clamp on; the engine launches the RTERM
-// variant only for a chunk whose imported state violates that.
-template <typename T, int NT, bool RTERM>
+__device__ __forceinline__ float flip_sign(float x, unsigned neg) { return __uint_as_float(__float_as_uint(x) ^ (neg << 31)); }
+__device__ __forceinline__ double flip_sign(double x, unsigned neg) {
+    return __hiloint2double(__double2hiint(x) ^ (int)(neg << 31), __double2loint(x));
+}
+__device__ __forceinline__ float fma_exact(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double fma_exact(double a, double b, double c) { return __fma_rn(a, b, c); }
+
+// The arithmetic of one clause for one replica (system.rs:43-88), two code paths that return
+// bit-identical results on the domain the integrator lives in:
+//   STRICT  the reference's statements one by one (sequential min / second-min, literal rigidity
+//           term).  Used for the first step after importing a state with some |v| > 1 or
+//           non-finite, or with a non-finite zeta.
+//   fast    valid when every v is finite in [-1, 1] (true after any clamp, system.rs:96) and
+//           zeta is finite:
+//             · 1 − q·v as one FMA (q = ±1 ⇒ the product is exact, so is the FMA)
+//             · min / second-min as a 5-op min/max network (order statistics do not depend
+//               on the evaluation order; no NaN can occur)
+//             · 0.5·q·sel·(xl·xs) as ±((0.5·xl·xs)·sel): scaling by ±0.5 commutes with rounding
+//             · the rigidity term dropped: it is ±0 and x + (±0) = x for every x the running
+//               sum can hold
+template <typename T, bool STRICT>
+__device__ __forceinline__ void clause_math(const T (&v)[3], T (&d)[3], const unsigned (&neg)[3], T& xs, T& xl, bool frozen,
+                                            bool& unsat, T dt, T zeta, T xl_max) {
+    const T hi_s = T(1) - Kc<T>::EPSILON;
+    T a[3], mn, sm;
+    if (STRICT) {
+        mn = inf_v<T>();
+        sm = inf_v<T>();
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const T q = neg[j] ? T(-1) : T(1);
+            a[j] = T(1) - q * v[j];                                         // :49
+            if (a[j] < mn) { sm = mn; mn = a[j]; } else if (a[j] < sm) { sm = a[j]; }   // :50-55
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) a[j] = fma_exact(neg[j] ? T(1) : T(-1), v[j], T(1));
+        const T lo = rmin(a[0], a[1]), hi = rmax(a[0], a[1]);
+        mn = rmin(lo, a[2]);
+        sm = rmax(lo, rmin(hi, a[2]));
+    }
+    const T cm = T(0.5) * mn;                                               // :60
+    const T wgt = xl * xs;
+    if (STRICT) {
+        const T rg = (T(1) + zeta * xl) * (T(1) - xs);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const T q = neg[j] ? T(-1) : T(1);
+            const T g = (T(0.5) * q) * ((a[j] != mn) ? mn : sm);            // :64-70
+            const T r = (cm == a[j]) ? T(0.5) * (q - v[j]) : T(0);          // :73-77
+            d[j] = d[j] + (wgt * g + rg * r);                               // :80
+        }
+    } else {
+        const T h = T(0.5) * wgt;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) d[j] = d[j] + flip_sign(h * ((a[j] != mn) ? mn : sm), neg[j]);
+    }
+    const T dxs = (Kc<T>::BETA * (xs + Kc<T>::EPSILON)) * (cm - Kc<T>::GAMMA);   // :84
+    const T dxl = Kc<T>::ALPHA * (cm - Kc<T>::DELTA);                            // :85
+    unsat = unsat || !(cm < Kc<T>::GAMMA);                                       // :88
+    if (!frozen) {
+        xs = euler_clamp(xs, dxs, dt, Kc<T>::EPSILON, hi_s);                     // :94
+        xl = euler_clamp(xl, dxl, dt, T(1), xl_max);                             // :95
+    }
+}
+
+// Asynchronous global→shared copies (LDGSTS) of the prefetch ring: no destination register and
+// no scoreboard slot, so — unlike a ring of plain loads, whose LDGs all share one of the six
+// per-warp scoreboards and therefore wait for each other — the copies really run D items ahead.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// One fused fixed Euler step per loop iteration, `nsteps` per launch; one CTA per replica tile.
+//
+// Work decomposition: the schedule is a sequence of ITEMS, each up to NT consecutive clause
+// slots of one level; thread t takes slot base + t when t < nvalid.  Every thread walks the
+// same item sequence, so the level barriers (after the last item of a level) are block-uniform.
+//
+// Latency hiding: a ring of D stages in shared memory, one 24-byte cell per thread and stage
+// ({xs, xl} of the slot + its packed clause).  As soon as a thread has consumed its cell of item
+// i it refills it with item i + D by cp.async (wrapping into the next Euler step), and waits
+// with cp.async.wait_group D−1 before reading item i.  A cell and a clause slot are only ever
+// touched by their own thread, so no barrier is involved.  NT·D·24 bytes are in flight per SM.
+// The schedule guarantees n_items % D == 0 and n_items > D.
+//
+// Shared memory:  rows[N] (16 B) | ring_m[D][NT] (16 B) | ring_e[D][NT] (8 B) | items[n_items]
+template <typename T, int NT, int D, bool STRICT>
 __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
     constexpr int W = TileTraits<T>::W;
     using Row = typename TileTraits<T>::Row;
@@ -80,15 +169,20 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
     using IO = RowIO<T, W>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Row* rows = reinterpret_cast<Row*>(smem_raw);
-    int32_t* s_goff = reinterpret_cast<int32_t*>(smem_raw + (size_t)a.N * sizeof(Row));
+    Mem* ring_m = reinterpret_cast<Mem*>(smem_raw + (size_t)a.N * sizeof(Row));
+    uint2* ring_e = reinterpret_cast<uint2*>(ring_m + D * NT);
+    uint32_t* s_items = reinterpret_cast<uint32_t*>(ring_e + D * NT);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = NT / 32;
+    const unsigned tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
     T* vt = a.vt + tile * a.N * W;
-    Mem* mem = a.mem + tile * a.Mpad;
+    Mem* my_mem = a.mem + tile * a.Mpad + tid;                                  // + slot base
+    const uint2* my_entry = reinterpret_cast<const uint2*>(a.entry) + tid;      // + slot base
+    Mem* my_cell_m = ring_m + tid;                                              // + k·NT
+    uint2* my_cell_e = ring_e + tid;
+    const int n_items = a.n_items;
 
-    for (int i = tid; i <= a.nlev; i += NT) s_goff[i] = a.goff[i];
+    for (int i = tid; i < n_items; i += NT) s_items[i] = a.items[i];
     for (int i = tid; i < a.N; i += NT) {
         T v[W], dv[W];
 #pragma unroll
@@ -104,90 +198,71 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
         frozen[w] = !valid[w] || (a.freeze && solved_at[w] >= 0);
     }
     __syncthreads();
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        const uint32_t it = s_items[k];
+        if (tid < ((it >> 20) & 0x7FFu)) {
+            cp_async16(my_cell_m + k * NT, my_mem + (it & 0xFFFFFu));
+            cp_async8(my_cell_e + k * NT, my_entry + (it & 0xFFFFFu));
+        }
+        cp_async_commit();
+    }
 
-    const T hi_s = T(1) - Kc<T>::EPSILON;
     for (int s = 0; s < a.nsteps; ++s) {
         bool all_frozen = true;
 #pragma unroll
         for (int w = 0; w < W; ++w) all_frozen = all_frozen && frozen[w];
         if (all_frozen) break;
-        unsigned unsat_bits = 0;
+        bool unsat[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) unsat[w] = false;
         // ------------------------------ clause phase -----------------------------------
-        // software prefetch: the packed clause and its memories for this warp's NEXT group are
-        // requested before the current group is processed (also across level barriers).
-        int lev = 0;
-        int g = s_goff[0] + warp;
-        while (lev < a.nlev && g >= s_goff[lev + 1]) { ++lev; g = s_goff[lev] + warp; }
-        uint64_t e_next = 0;
-        Mem m_next;
-        if (lev < a.nlev) {
-            const int64_t c = (int64_t)g * 32 + lane;
-            e_next = __ldg(a.entry + c);
-            m_next = mem[c];
-        }
-        for (int L = 0; L < a.nlev; ++L) {
-            while (lev == L) {
-                const int64_t c = (int64_t)g * 32 + lane;
-                const uint64_t e = e_next;
-                const Mem mm = m_next;
-                // advance to this warp's next group and issue its loads
-                g += NW;
-                while (lev < a.nlev && g >= s_goff[lev + 1]) { ++lev; if (lev < a.nlev) g = s_goff[lev] + warp; }
-                if (lev < a.nlev) {
-                    const int64_t cn = (int64_t)g * 32 + lane;
-                    e_next = __ldg(a.entry + cn);
-                    m_next = mem[cn];
-                }
-                if (e & TILE_VALID_BIT) {
-                    const int i0 = (int)(e & 0xFFFF), i1 = (int)((e >> 16) & 0xFFFF), i2 = (int)((e >> 32) & 0xFFFF);
-                    const T q0 = (e >> 48) & 1 ? T(-1) : T(1), q1 = (e >> 49) & 1 ? T(-1) : T(1), q2 = (e >> 50) & 1 ? T(-1) : T(1);
-                    T v0[W], v1[W], v2[W], d0[W], d1[W], d2[W], xs[W], xl[W];
-                    IO::unpack(rows[i0], v0, d0);
-                    IO::unpack(rows[i1], v1, d1);
-                    IO::unpack(rows[i2], v2, d2);
+        for (int base = 0; base < n_items; base += D) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                const int i = base + k;
+                const uint32_t it = s_items[i];
+                cp_async_wait<D - 1>();                     // this thread's cell of item i has landed
+                if (tid < ((it >> 20) & 0x7FFu)) {
+                    const uint2 e = my_cell_e[k * NT];
+                    const Mem mm = my_cell_m[k * NT];
+                    const unsigned i0 = e.x & 0xFFFFu, i1 = e.x >> 16, i2 = e.y & 0xFFFFu;
+                    const unsigned neg[3] = {(e.y >> 16) & 1u, (e.y >> 17) & 1u, (e.y >> 18) & 1u};
+                    T v[3][W], d[3][W], xs[W], xl[W];
+                    IO::unpack(rows[i0], v[0], d[0]);
+                    IO::unpack(rows[i1], v[1], d[1]);
+                    IO::unpack(rows[i2], v[2], d[2]);
                     IO::unpack_mem(mm, xs, xl);
 #pragma unroll
                     for (int w = 0; w < W; ++w) {
-                        // system.rs:46-57 (q = ±1, so q·v is exact)
-                        const T a0 = T(1) - q0 * v0[w], a1 = T(1) - q1 * v1[w], a2 = T(1) - q2 * v2[w];
-                        T mn = inf_v<T>(), sm = inf_v<T>();
-                        if (a0 < mn) { sm = mn; mn = a0; } else if (a0 < sm) { sm = a0; }
-                        if (a1 < mn) { sm = mn; mn = a1; } else if (a1 < sm) { sm = a1; }
-                        if (a2 < mn) { sm = mn; mn = a2; } else if (a2 < sm) { sm = a2; }
-                        const T cm = T(0.5) * mn;                                        // :60
-                        const T wgt = xl[w] * xs[w];
-                        T t0 = wgt * ((T(0.5) * q0) * ((a0 != mn) ? mn : sm));           // :64-70, :80
-                        T t1 = wgt * ((T(0.5) * q1) * ((a1 != mn) ? mn : sm));
-                        T t2 = wgt * ((T(0.5) * q2) * ((a2 != mn) ? mn : sm));
-                        if (RTERM) {
-                            const T rg = (T(1) + a.zeta * xl[w]) * (T(1) - xs[w]);
-                            t0 = t0 + rg * ((cm == a0) ? T(0.5) * (q0 - v0[w]) : T(0));  // :73-77
-                            t1 = t1 + rg * ((cm == a1) ? T(0.5) * (q1 - v1[w]) : T(0));
-                            t2 = t2 + rg * ((cm == a2) ? T(0.5) * (q2 - v2[w]) : T(0));
-                        }
-                        d0[w] = d0[w] + t0;
-                        d1[w] = d1[w] + t1;
-                        d2[w] = d2[w] + t2;
-                        const T dxs = (Kc<T>::BETA * (xs[w] + Kc<T>::EPSILON)) * (cm - Kc<T>::GAMMA);   // :84
-                        const T dxl = Kc<T>::ALPHA * (cm - Kc<T>::DELTA);                                // :85
-                        if (!(cm < Kc<T>::GAMMA)) unsat_bits |= 1u << w;                                 // :88
-                        if (!frozen[w]) {
-                            xs[w] = euler_clamp(xs[w], dxs, a.dt, Kc<T>::EPSILON, hi_s);                // :94
-                            xl[w] = euler_clamp(xl[w], dxl, a.dt, T(1), a.xl_max);                      // :95
-                        }
+                        const T vv[3] = {v[0][w], v[1][w], v[2][w]};
+                        T dd[3] = {d[0][w], d[1][w], d[2][w]};
+                        clause_math<T, STRICT>(vv, dd, neg, xs[w], xl[w], frozen[w], unsat[w], a.dt, a.zeta, a.xl_max);
+                        d[0][w] = dd[0]; d[1][w] = dd[1]; d[2][w] = dd[2];
                     }
-                    IO::store_dv(rows + i0, d0);
-                    IO::store_dv(rows + i1, d1);
-                    IO::store_dv(rows + i2, d2);
-                    mem[c] = IO::pack_mem(xs, xl);
+                    // full-row stores: an 8-byte store of the dv half alone is a 2-way bank conflict
+                    rows[i0] = IO::pack(v[0], d[0]);
+                    rows[i1] = IO::pack(v[1], d[1]);
+                    rows[i2] = IO::pack(v[2], d[2]);
+                    __stcg(my_mem + (it & 0xFFFFFu), IO::pack_mem(xs, xl));
                 }
+                {   // refill cell k with item i + D (next step's item i + D − n_items at the end)
+                    int nx = i + D;
+                    if (nx >= n_items) nx -= n_items;
+                    const uint32_t itn = s_items[nx];
+                    if (tid < ((itn >> 20) & 0x7FFu)) {
+                        cp_async16(my_cell_m + k * NT, my_mem + (itn & 0xFFFFFu));
+                        cp_async8(my_cell_e + k * NT, my_entry + (itn & 0xFFFFFu));
+                    }
+                    cp_async_commit();
+                }
+                if (it & TILE_ITEM_LAST) __syncthreads();   // end of a level: block-uniform
             }
-            __syncthreads();
         }
         // ------------------------------ flags + variable phase ---------------------------
         unsigned any_unsat = 0;   // __syncthreads_or is a boolean OR: one call per replica of the tile
 #pragma unroll
-        for (int w = 0; w < W; ++w) any_unsat |= (__syncthreads_or((int)((unsat_bits >> w) & 1u)) ? 1u : 0u) << w;
+        for (int w = 0; w < W; ++w) any_unsat |= (__syncthreads_or((int)unsat[w]) ? 1u : 0u) << w;
         for (int i = tid; i < a.N; i += NT) {
             T v[W], dv[W];
             IO::unpack(rows[i], v, dv);
@@ -211,6 +286,7 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
         }
         __syncthreads();
     }
+    cp_async_wait<0>();
     for (int i = tid; i < a.N; i += NT) {
         T v[W], dv[W];
         IO::unpack(rows[i], v, dv);
@@ -236,7 +312,7 @@ __global__ void k_tile_import(const T* __restrict__ v, const T* __restrict__ xs,
             const int64_t r = tile * W + w;
             const T x = r < R ? v[row * Rp + r] : T(0);
             vt[(tile * N + row) * W + w] = x;
-            bad = bad || fabs(x) > T(1);
+            bad = bad || !(fabs(x) <= T(1));   // |v| > 1 or NaN
         }
         if (bad) *out_of_range = 1u;
     } else {
@@ -296,10 +372,19 @@ template <typename T> struct TileEngine {
     DevBuf<Mem> mem;
     DevBuf<unsigned> oor;
     bool need_rterm = true;
-    int nt = 1024;
+    int nt = 512;
     int chunk = 64;   // Euler steps per launch
+    int depth = 6;    // prefetch ring depth (tunable for NT = 512 only)
 
-    static size_t smem_bytes(int64_t N, int nlev) { return (size_t)N * 16 + (size_t)(nlev + 2) * 4; }
+    static size_t smem_bytes(int64_t N, int n_items, int nt, int depth) {
+        return (size_t)N * 16 + (size_t)nt * depth * 24 + (size_t)(n_items + 2) * 4;
+    }
+    // deepest ring (≤ 6) that fits beside the variable rows
+    static int pick_depth(int64_t N, int nt, int n_items_guess) {
+        for (int d = 6; d >= 2; --d)
+            if (smem_bytes(N, n_items_guess, nt, d) <= kMaxSmem) return d;
+        return 0;
+    }
 
     static bool supports(const odesat_formula& f, int64_t R, std::string* why) {
         auto no = [&](const char* m) { if (why) *why = m; return false; };
@@ -307,22 +392,45 @@ template <typename T> struct TileEngine {
         if (f.K != 3) return no("needs uniform clause length 3");
         if (!f.distinct_vars) return no("a clause repeats a variable");
         if (f.N > 65535) return no("more than 65535 variables");
-        if (smem_bytes(f.N, 4096) > kMaxSmem) return no("variables do not fit in 227 KB of shared memory");
+        if (pick_depth(f.N, 128, 4096) < 2) return no("variables do not fit in 227 KB of shared memory");
         return true;
     }
     static bool preferred(const odesat_formula&, int64_t R) { return R >= 8; }
 
     TileEngine(const odesat_formula& f_, int64_t R_, int kind, cudaStream_t st, int64_t* ledger) : f(f_), R(R_), stream(st) {
         tiles = (R + W - 1) / W;
-        auto it = f.tile_sched.find(kind);
-        if (it == f.tile_sched.end()) it = f.tile_sched.emplace(kind, build_tile_schedule(f, kind)).first;
+        auto lv = f.tile_levels.find(kind);
+        if (lv == f.tile_levels.end()) lv = f.tile_levels.emplace(kind, build_tile_levels(f, kind)).first;
+        // CTA width: wide enough that a typical level is one item; small formulas get a narrow CTA
+        std::vector<size_t> sizes;
+        for (const auto& b : lv->second->bucket) if (!b.empty()) sizes.push_back(b.size());
+        std::sort(sizes.begin(), sizes.end());
+        const size_t median = sizes.empty() ? 0 : sizes[sizes.size() / 2];
+        nt = median > 128 ? 512 : 128;
+        static const int cand[] = {128, 512, 1024};
+        if (const char* e = std::getenv("ODESAT_TILE_NT")) {
+            const int v = std::atoi(e);
+            for (int c : cand) if (v == c) nt = v;
+        }
+        if (const char* e = std::getenv("ODESAT_TILE_CHUNK")) { const int v = std::atoi(e); if (v > 0) chunk = v; }
+        int want = 0;
+        if (const char* e = std::getenv("ODESAT_TILE_D")) want = std::atoi(e);
+        for (;;) {   // widest CTA first; fall back to a narrower one if its ring does not fit
+            const int guess = (int)(f.M / nt + 3 * (int64_t)lv->second->bucket.size() + 16);
+            depth = pick_depth(f.N, nt, guess);
+            if (depth >= 2 || nt == 128) break;
+            nt = nt == 1024 ? 512 : 128;
+        }
+        if (depth < 2) throw Error(ODESAT_EUNSUPPORTED, "variables do not fit in shared memory");
+        if (want >= 2 && want <= depth) depth = want;
+        const int key = (kind * 64 + nt / 32) * 16 + depth;
+        auto it = f.tile_sched.find(key);
+        if (it == f.tile_sched.end()) it = f.tile_sched.emplace(key, build_tile_schedule(f, *lv->second, kind, nt, (depth % 2) ? 2 * depth : depth)).first;
         sched = it->second;
-        if (smem_bytes(f.N, sched->nlev) > kMaxSmem) throw Error(ODESAT_EUNSUPPORTED, "schedule does not fit in shared memory");
+        if (smem_bytes(f.N, sched->n_items, nt, depth) > kMaxSmem) throw Error(ODESAT_EUNSUPPORTED, "schedule does not fit in shared memory");
         vt.alloc((size_t)(tiles * f.N * W), ledger);
         mem.alloc((size_t)(tiles * sched->Mpad), ledger);
         oor.alloc(1, ledger);
-        if (const char* e = std::getenv("ODESAT_TILE_NT")) { const int v = std::atoi(e); if (v == 256 || v == 512 || v == 1024) nt = v; }
-        if (const char* e = std::getenv("ODESAT_TILE_CHUNK")) { const int v = std::atoi(e); if (v > 0) chunk = v; }
     }
     void reset_control() { need_rterm = true; }
 
@@ -354,19 +462,29 @@ template <typename T> struct TileEngine {
         return 1;
     }
 
-    template <int NT, bool RTERM> void launch(const TileArgs<T>& a) {
-        const size_t smem = smem_bytes(f.N, sched->nlev);
+    template <int NT, int D, bool STRICT> void launch(const TileArgs<T>& a) {
+        const size_t smem = smem_bytes(f.N, sched->n_items, NT, D);
         static bool attr_set = false;   // per instantiation
         if (!attr_set) {
-            ODESAT_CUDA(cudaFuncSetAttribute(k_tile_fixed<T, NT, RTERM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+            ODESAT_CUDA(cudaFuncSetAttribute(k_tile_fixed<T, NT, D, STRICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
             attr_set = true;
         }
-        k_tile_fixed<T, NT, RTERM><<<(unsigned)tiles, NT, smem, stream>>>(a);
+        k_tile_fixed<T, NT, D, STRICT><<<(unsigned)tiles, NT, smem, stream>>>(a);
     }
-    template <bool RTERM> void launch_nt(const TileArgs<T>& a) {
-        if (nt == 1024) launch<1024, RTERM>(a);
-        else if (nt == 512) launch<512, RTERM>(a);
-        else launch<256, RTERM>(a);
+    template <int NT> void launch_d(const TileArgs<T>& a, bool strict) {
+        if (strict) { launch<NT, 2, true>(a); return; }   // ring of 2 divides every schedule padding
+        switch (depth) {
+            case 2: launch<NT, 2, false>(a); break;
+            case 3: launch<NT, 3, false>(a); break;
+            case 4: launch<NT, 4, false>(a); break;
+            case 5: launch<NT, 5, false>(a); break;
+            default: launch<NT, 6, false>(a); break;
+        }
+    }
+    void launch_nt(const TileArgs<T>& a, bool strict) {
+        if (nt == 128) launch_d<128>(a, strict);
+        else if (nt == 512) launch_d<512>(a, strict);
+        else launch_d<1024>(a, strict);
     }
 
     int64_t run_fixed(T dt, T zeta, int64_t n, int freeze, int32_t* solved, int64_t step0) {
@@ -375,19 +493,19 @@ template <typename T> struct TileEngine {
         for (int64_t done = 0; done < n;) {
             const int64_t k = std::min<int64_t>(chunk, n - done);
             TileArgs<T> a;
-            a.N = f.N; a.Mpad = sched->Mpad; a.R = R; a.nlev = sched->nlev;
-            a.goff = sched->d_goff.p; a.entry = sched->d_entry.p;
+            a.N = f.N; a.Mpad = sched->Mpad; a.R = R; a.n_items = sched->n_items;
+            a.items = sched->d_items.p; a.entry = sched->d_entry.p;
             a.vt = vt.p; a.mem = mem.p; a.solved = solved;
             a.dt = dt; a.zeta = zeta; a.xl_max = T(1e4) * T(f.M);
             a.step0 = (int32_t)(step0 + done); a.nsteps = (int32_t)k; a.freeze = freeze;
             if (need_rterm || !zeta_ok) {
                 // only the first step can see |v| > 1; run it alone with the literal rigidity term
                 a.nsteps = 1;
-                launch_nt<true>(a);
+                launch_nt(a, true);
                 done += 1;
                 if (zeta_ok) need_rterm = false;
             } else {
-                launch_nt<false>(a);
+                launch_nt(a, false);
                 done += k;
             }
             ++launches;

@@ -27,15 +27,26 @@
 
 namespace odesat {
 
+// An ITEM is up to NT consecutive slots of one level, processed by the CTA in lock-step (thread
+// t takes slot base + t when t < nvalid).  Packed as base (20 bits) | nvalid (11 bits) << 20 |
+// last-item-of-level << 31.
+constexpr uint32_t TILE_ITEM_LAST = 1u << 31;
+inline uint32_t pack_item(uint32_t base, uint32_t nvalid, bool last) {
+    return base | (nvalid << 20) | (last ? TILE_ITEM_LAST : 0u);
+}
+
 struct TileSchedule {
     int kind = 0;
-    int64_t M = 0, Mpad = 0;           // real clauses, padded slots (multiple of 32)
+    int nt = 0;                        // threads per CTA the items were cut for
+    int64_t M = 0, Mpad = 0;           // real clauses, slots (levels padded to 8 slots = 128 B)
     int nlev = 0;
-    std::vector<int32_t> goff;         // [nlev+1] level boundaries in groups of 32 slots
+    int n_items = 0;
+    std::vector<uint32_t> items;       // [n_items] packed (base, nvalid, last)
     std::vector<int32_t> perm;         // [Mpad] slot → clause index, −1 = padding
     std::vector<uint64_t> entry;       // [Mpad] packed clause: 3×16-bit row + sign bits + valid
     double conflict_wavefronts = 0;    // avg shared-memory wavefronts per quarter-warp access (1 = ideal)
-    DevBuf<int32_t> d_goff, d_perm;
+    DevBuf<int32_t> d_perm;
+    DevBuf<uint32_t> d_items;
     DevBuf<uint64_t> d_entry;
 };
 
@@ -123,10 +134,14 @@ inline void pack_level(const odesat_formula& f, const std::vector<int32_t>& clau
     }
 }
 
-inline std::shared_ptr<TileSchedule> build_tile_schedule(const odesat_formula& f, int kind) {
-    auto s = std::make_shared<TileSchedule>();
-    s->kind = kind;
-    s->M = f.M;
+// Level assignment only (shared by every warp count); cached on the formula.
+struct TileLevels {
+    int nlev = 0;
+    std::vector<std::vector<int32_t>> bucket;   // clauses of each level, ascending index
+};
+
+inline std::shared_ptr<TileLevels> build_tile_levels(const odesat_formula& f, int kind) {
+    auto s = std::make_shared<TileLevels>();
     const int64_t M = f.M, N = f.N;
     std::vector<int32_t> level(M, 0);
     int nlev = 0;
@@ -144,8 +159,10 @@ inline std::shared_ptr<TileSchedule> build_tile_schedule(const odesat_formula& f
             nlev = std::max(nlev, lv + 1);
         }
     } else {
-        // target: levels of ~1024 clauses, but never fewer colours than the max variable degree
+        // target: levels of 1024 clauses (a whole number of 512-thread items), but never fewer
+        // colours than the max variable degree; classes are capped at a multiple of 512
         int C = (int)std::max<int64_t>(f.max_degree + 2, (M + 1023) / 1024);
+        const int cap = (int)(((M + C - 1) / C + 511) / 512 * 512);
         std::vector<std::vector<uint64_t>> usedc;   // per variable: bitset of colours taken
         int words = (C + 63 + 64) / 64;             // slack for overflow colours
         std::vector<uint64_t> bits((size_t)N * words, 0);
@@ -168,7 +185,7 @@ inline std::shared_ptr<TileSchedule> build_tile_schedule(const odesat_formula& f
             int best = -1, bl = INT32_MAX;
             for (int c = 0; c < ncol; ++c) {
                 const uint64_t forb = b0[c >> 6] | b1[c >> 6] | b2[c >> 6];
-                if (!((forb >> (c & 63)) & 1) && load[c] < bl) { best = c; bl = load[c]; }
+                if (!((forb >> (c & 63)) & 1) && load[c] < bl && load[c] < cap) { best = c; bl = load[c]; }
             }
             if (best < 0) {
                 if (ncol >= words * 64) throw Error(ODESAT_EINVAL, "balanced schedule ran out of colours");
@@ -180,26 +197,44 @@ inline std::shared_ptr<TileSchedule> build_tile_schedule(const odesat_formula& f
         }
         nlev = ncol;
     }
-    // bucket by level (stable in clause index), pack each level, pad to whole groups of 32
-    std::vector<std::vector<int32_t>> bucket(nlev);
-    for (int64_t m = 0; m < M; ++m) bucket[level[m]].push_back((int32_t)m);
-    s->goff.assign(1, 0);
+    s->nlev = nlev;
+    s->bucket.assign(nlev, {});
+    for (int64_t m = 0; m < M; ++m) s->bucket[level[m]].push_back((int32_t)m);
+    return s;
+}
+
+// `depth`: prefetch ring depth of the kernel the schedule is for; the item list is padded with
+// empty items to a multiple of it (and to more than one ring) so that item i always lives in
+// ring slot i % depth and a slot is stored before it is prefetched again.
+inline std::shared_ptr<TileSchedule> build_tile_schedule(const odesat_formula& f, const TileLevels& lv, int kind, int nt, int depth) {
+    auto s = std::make_shared<TileSchedule>();
+    s->kind = kind;
+    s->nt = nt;
+    s->M = f.M;
     double wsum = 0;
     int64_t wcnt = 0;
-    for (int lv = 0; lv < nlev; ++lv) {
-        if (bucket[lv].empty()) continue;
-        pack_level(f, bucket[lv], s->perm, s->entry, wsum, wcnt);
-        while (s->perm.size() % 32) { s->perm.push_back(-1); s->entry.push_back(0); }
-        s->goff.push_back((int32_t)(s->perm.size() / 32));
+    for (const auto& b : lv.bucket) {
+        if (b.empty()) continue;
+        const size_t base0 = s->perm.size();
+        pack_level(f, b, s->perm, s->entry, wsum, wcnt);
+        const size_t n = s->perm.size() - base0;
+        while (s->perm.size() % 8) { s->perm.push_back(-1); s->entry.push_back(0); }
+        for (size_t o = 0; o < n; o += (size_t)nt) {
+            const size_t cnt = std::min<size_t>((size_t)nt, n - o);
+            s->items.push_back(pack_item((uint32_t)(base0 + o), (uint32_t)cnt, o + (size_t)nt >= n));
+        }
+        ++s->nlev;
     }
-    s->nlev = (int)s->goff.size() - 1;
+    while (s->items.size() % (size_t)depth || s->items.size() <= (size_t)depth) s->items.push_back(pack_item(0, 0, false));
     s->Mpad = (int64_t)s->perm.size();
+    if (s->Mpad >= (1 << 20)) throw Error(ODESAT_EUNSUPPORTED, "tile schedule: more than 2^20 clause slots");
+    s->n_items = (int)s->items.size();
     s->conflict_wavefronts = wcnt ? wsum / wcnt : 1.0;
-    s->d_goff.alloc(s->goff.size());
+    s->d_items.alloc(std::max<size_t>(s->items.size(), 1));
     s->d_perm.alloc(std::max<size_t>(s->perm.size(), 1));
     s->d_entry.alloc(std::max<size_t>(s->entry.size(), 1));
-    ODESAT_CUDA(cudaMemcpy(s->d_goff.p, s->goff.data(), s->goff.size() * 4, cudaMemcpyHostToDevice));
     if (!s->perm.empty()) {
+        ODESAT_CUDA(cudaMemcpy(s->d_items.p, s->items.data(), s->items.size() * 4, cudaMemcpyHostToDevice));
         ODESAT_CUDA(cudaMemcpy(s->d_perm.p, s->perm.data(), s->perm.size() * 4, cudaMemcpyHostToDevice));
         ODESAT_CUDA(cudaMemcpy(s->d_entry.p, s->entry.data(), s->entry.size() * 8, cudaMemcpyHostToDevice));
     }
