@@ -182,6 +182,17 @@ int odesat_simulate_inter(const odesat_formula* f, int64_t R, double* v, double*
                           const odesat_params* params, uint8_t* assignment, int64_t* winner,
                           int64_t* steps_taken);
 
+/* ---- diagnostics (host only, no device needed) -------------------------------------------------
+ * Compiles the TILE engine's clause schedule for a formula and reports it: out[0] = levels,
+ * out[1] = items, out[2] = clause slots (incl. padding), out[3] = 1000 x the average number of
+ * shared-memory wavefronts per quarter-warp row access (1000 = conflict-free).  perm (optional,
+ * capacity >= out[2]) receives slot -> clause index (-1 = padding); items (optional, capacity >=
+ * out[1]) the packed item words (slot base | count << 20 | last-of-level << 31). */
+int odesat_tile_schedule_stats(int64_t varnum, int64_t n_clauses, const int64_t* clause_off,
+                               const int32_t* lits, int32_t schedule, int32_t threads, int32_t depth,
+                               int32_t* perm, int64_t perm_capacity, uint32_t* items,
+                               int64_t items_capacity, int64_t* out);
+
 /* ---- device-resident batch object (what the calls above are built from; used by the
  *      multi-GPU host layer and the benchmark to keep state in HBM between calls) ------------- */
 int odesat_batch_create(const odesat_formula* f, int64_t R, int32_t precision, int32_t engine,

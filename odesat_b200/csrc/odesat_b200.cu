@@ -359,6 +359,33 @@ int odesat_simulate_inter(const odesat_formula* f, int64_t R, double* v, double*
     });
 }
 
+int odesat_tile_schedule_stats(int64_t varnum, int64_t n_clauses, const int64_t* clause_off, const int32_t* lits,
+                               int32_t schedule, int32_t threads, int32_t depth, int32_t* perm, int64_t perm_capacity,
+                               uint32_t* items, int64_t items_capacity, int64_t* out) {
+    return guarded([&] {
+        ODESAT_REQUIRE(out != nullptr, "out is NULL");
+        ODESAT_REQUIRE(schedule == ODESAT_SCHED_EXACT || schedule == ODESAT_SCHED_BALANCED, "unknown schedule");
+        ODESAT_REQUIRE(threads >= 32 && threads <= 1024 && threads % 32 == 0 && depth >= 1 && depth <= 16, "bad threads/depth");
+        odesat_formula f;
+        f.build(varnum, n_clauses, clause_off, lits);
+        ODESAT_REQUIRE(f.K == 3 && f.distinct_vars, "tile schedules need uniform 3-literal clauses with distinct variables");
+        auto lv = build_tile_levels(f, schedule);
+        auto s = build_tile_schedule(f, *lv, schedule, threads, depth, /*upload=*/false);
+        out[0] = s->nlev;
+        out[1] = s->n_items;
+        out[2] = s->Mpad;
+        out[3] = (int64_t)(s->conflict_wavefronts * 1000.0 + 0.5);
+        if (perm) {
+            ODESAT_REQUIRE(perm_capacity >= s->Mpad, "perm buffer too small");
+            for (int64_t i = 0; i < s->Mpad; ++i) perm[i] = s->perm[i];
+        }
+        if (items) {
+            ODESAT_REQUIRE(items_capacity >= s->n_items, "items buffer too small");
+            for (int64_t i = 0; i < s->n_items; ++i) items[i] = s->items[i];
+        }
+    });
+}
+
 int odesat_batch_create(const odesat_formula* f, int64_t R, int32_t precision, int32_t engine, int32_t schedule,
                         odesat_batch** out) {
     return guarded([&] {

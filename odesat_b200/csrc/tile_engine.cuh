@@ -144,6 +144,16 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
+// Full 16-byte row store.  Written as volatile asm so that the compiler cannot shrink it to an
+// 8-byte store of the dv half: 16 lanes × 8 B at stride 16 is an unavoidable 2-way bank
+// conflict, whereas the 128-bit store is served per quarter-warp and is conflict-free whenever
+// the octet's rows are distinct mod 8 (what the schedule packer arranges).
+__device__ __forceinline__ void st_row(float4* p, const float4& r) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"((unsigned)__cvta_generic_to_shared(p)), "f"(r.x), "f"(r.y), "f"(r.z), "f"(r.w) : "memory");
+}
+__device__ __forceinline__ void st_row(double2* p, const double2& r) {
+    asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"((unsigned)__cvta_generic_to_shared(p)), "d"(r.x), "d"(r.y) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -153,15 +163,21 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // slots of one level; thread t takes slot base + t when t < nvalid.  Every thread walks the
 // same item sequence, so the level barriers (after the last item of a level) are block-uniform.
 //
-// Latency hiding: a ring of D stages in shared memory, one 24-byte cell per thread and stage
-// ({xs, xl} of the slot + its packed clause).  As soon as a thread has consumed its cell of item
-// i it refills it with item i + D by cp.async (wrapping into the next Euler step), and waits
-// with cp.async.wait_group D−1 before reading item i.  A cell and a clause slot are only ever
-// touched by their own thread, so no barrier is involved.  NT·D·24 bytes are in flight per SM.
+// Latency hiding: a ring of D stages in shared memory, one 16-byte cell per thread and stage
+// ({xs, xl} of the thread's slot, the HBM stream).  As soon as a thread has consumed its cell of
+// item i it refills it with item i + D by cp.async (wrapping into the next Euler step), and
+// waits with cp.async.wait_group D−1 before reading item i.  A cell and a clause slot are only
+// ever touched by their own thread, so no barrier is involved.  NT·D·16 bytes are in flight per
+// SM.  The packed clause (8 B, identical for every CTA, L2-resident) is loaded into registers one
+// item ahead — a single outstanding LDG, so no scoreboard aliasing.
 // The schedule guarantees n_items % D == 0 and n_items > D.
 //
-// Shared memory:  rows[N] (16 B) | ring_m[D][NT] (16 B) | ring_e[D][NT] (8 B) | items[n_items]
-template <typename T, int NT, int D, bool STRICT>
+// Shared memory:  rows[N] (16 B) | ring_m[D][NT] (16 B) | items[n_items]
+//
+// ER (entry-in-ring): the packed clause word travels through the cp.async ring too (24-byte
+// cells) instead of the 1-ahead register load.  Better when an item is short (narrow CTA): one
+// item time does not always cover an L2 round trip.
+template <typename T, int NT, int D, bool STRICT, bool ER>
 __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
     constexpr int W = TileTraits<T>::W;
     using Row = typename TileTraits<T>::Row;
@@ -171,7 +187,7 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
     Row* rows = reinterpret_cast<Row*>(smem_raw);
     Mem* ring_m = reinterpret_cast<Mem*>(smem_raw + (size_t)a.N * sizeof(Row));
     uint2* ring_e = reinterpret_cast<uint2*>(ring_m + D * NT);
-    uint32_t* s_items = reinterpret_cast<uint32_t*>(ring_e + D * NT);
+    uint32_t* s_items = reinterpret_cast<uint32_t*>(ring_e + (ER ? D * NT : 0));
 
     const unsigned tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
@@ -203,10 +219,13 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
         const uint32_t it = s_items[k];
         if (tid < ((it >> 20) & 0x7FFu)) {
             cp_async16(my_cell_m + k * NT, my_mem + (it & 0xFFFFFu));
-            cp_async8(my_cell_e + k * NT, my_entry + (it & 0xFFFFFu));
+            if (ER) cp_async8(my_cell_e + k * NT, my_entry + (it & 0xFFFFFu));
         }
         cp_async_commit();
     }
+    uint32_t it_next = s_items[0];
+    uint2 e_next = make_uint2(0u, 0u);
+    if (!ER && tid < ((it_next >> 20) & 0x7FFu)) e_next = __ldg(my_entry + (it_next & 0xFFFFFu));
 
     for (int s = 0; s < a.nsteps; ++s) {
         bool all_frozen = true;
@@ -221,10 +240,17 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
 #pragma unroll
             for (int k = 0; k < D; ++k) {
                 const int i = base + k;
-                const uint32_t it = s_items[i];
+                const uint32_t it = it_next;
+                uint2 e = e_next;
+                {   // descriptor (and, without ER, packed clause) of the NEXT item, wrapping into the next step
+                    const int i1 = (i + 1 == n_items) ? 0 : i + 1;
+                    it_next = s_items[i1];
+                    if (!ER && tid < ((it_next >> 20) & 0x7FFu)) e_next = __ldg(my_entry + (it_next & 0xFFFFFu));
+                }
                 cp_async_wait<D - 1>();                     // this thread's cell of item i has landed
-                if (tid < ((it >> 20) & 0x7FFu)) {
-                    const uint2 e = my_cell_e[k * NT];
+                const bool mine = tid < ((it >> 20) & 0x7FFu);
+                if (ER && mine) e = my_cell_e[k * NT];
+                if (mine && (e.y & (unsigned)(TILE_VALID_BIT >> 32))) {
                     const Mem mm = my_cell_m[k * NT];
                     const unsigned i0 = e.x & 0xFFFFu, i1 = e.x >> 16, i2 = e.y & 0xFFFFu;
                     const unsigned neg[3] = {(e.y >> 16) & 1u, (e.y >> 17) & 1u, (e.y >> 18) & 1u};
@@ -241,9 +267,9 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
                         d[0][w] = dd[0]; d[1][w] = dd[1]; d[2][w] = dd[2];
                     }
                     // full-row stores: an 8-byte store of the dv half alone is a 2-way bank conflict
-                    rows[i0] = IO::pack(v[0], d[0]);
-                    rows[i1] = IO::pack(v[1], d[1]);
-                    rows[i2] = IO::pack(v[2], d[2]);
+                    st_row(rows + i0, IO::pack(v[0], d[0]));
+                    st_row(rows + i1, IO::pack(v[1], d[1]));
+                    st_row(rows + i2, IO::pack(v[2], d[2]));
                     __stcg(my_mem + (it & 0xFFFFFu), IO::pack_mem(xs, xl));
                 }
                 {   // refill cell k with item i + D (next step's item i + D − n_items at the end)
@@ -252,7 +278,7 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
                     const uint32_t itn = s_items[nx];
                     if (tid < ((itn >> 20) & 0x7FFu)) {
                         cp_async16(my_cell_m + k * NT, my_mem + (itn & 0xFFFFFu));
-                        cp_async8(my_cell_e + k * NT, my_entry + (itn & 0xFFFFFu));
+                        if (ER) cp_async8(my_cell_e + k * NT, my_entry + (itn & 0xFFFFFu));
                     }
                     cp_async_commit();
                 }
@@ -376,8 +402,9 @@ template <typename T> struct TileEngine {
     int chunk = 64;   // Euler steps per launch
     int depth = 6;    // prefetch ring depth (tunable for NT = 512 only)
 
+    static bool entry_in_ring(int nt) { return nt < 1024; }
     static size_t smem_bytes(int64_t N, int n_items, int nt, int depth) {
-        return (size_t)N * 16 + (size_t)nt * depth * 24 + (size_t)(n_items + 2) * 4;
+        return (size_t)N * 16 + (size_t)nt * depth * (entry_in_ring(nt) ? 24 : 16) + (size_t)(n_items + 2) * 4;
     }
     // deepest ring (≤ 6) that fits beside the variable rows
     static int pick_depth(int64_t N, int nt, int n_items_guess) {
@@ -406,7 +433,7 @@ template <typename T> struct TileEngine {
         for (const auto& b : lv->second->bucket) if (!b.empty()) sizes.push_back(b.size());
         std::sort(sizes.begin(), sizes.end());
         const size_t median = sizes.empty() ? 0 : sizes[sizes.size() / 2];
-        nt = median > 128 ? 512 : 128;
+        nt = median > 640 ? 1024 : (median > 128 ? 512 : 128);
         static const int cand[] = {128, 512, 1024};
         if (const char* e = std::getenv("ODESAT_TILE_NT")) {
             const int v = std::atoi(e);
@@ -425,7 +452,7 @@ template <typename T> struct TileEngine {
         if (want >= 2 && want <= depth) depth = want;
         const int key = (kind * 64 + nt / 32) * 16 + depth;
         auto it = f.tile_sched.find(key);
-        if (it == f.tile_sched.end()) it = f.tile_sched.emplace(key, build_tile_schedule(f, *lv->second, kind, nt, (depth % 2) ? 2 * depth : depth)).first;
+        if (it == f.tile_sched.end()) it = f.tile_sched.emplace(key, build_tile_schedule(f, *lv->second, kind, nt, depth)).first;
         sched = it->second;
         if (smem_bytes(f.N, sched->n_items, nt, depth) > kMaxSmem) throw Error(ODESAT_EUNSUPPORTED, "schedule does not fit in shared memory");
         vt.alloc((size_t)(tiles * f.N * W), ledger);
@@ -466,10 +493,10 @@ template <typename T> struct TileEngine {
         const size_t smem = smem_bytes(f.N, sched->n_items, NT, D);
         static bool attr_set = false;   // per instantiation
         if (!attr_set) {
-            ODESAT_CUDA(cudaFuncSetAttribute(k_tile_fixed<T, NT, D, STRICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+            ODESAT_CUDA(cudaFuncSetAttribute(k_tile_fixed<T, NT, D, STRICT, (NT < 1024)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
             attr_set = true;
         }
-        k_tile_fixed<T, NT, D, STRICT><<<(unsigned)tiles, NT, smem, stream>>>(a);
+        k_tile_fixed<T, NT, D, STRICT, (NT < 1024)><<<(unsigned)tiles, NT, smem, stream>>>(a);
     }
     template <int NT> void launch_d(const TileArgs<T>& a, bool strict) {
         if (strict) { launch<NT, 2, true>(a); return; }   // ring of 2 divides every schedule padding

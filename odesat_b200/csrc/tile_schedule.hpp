@@ -61,76 +61,100 @@ inline uint64_t pack_entry3(const int32_t* var, const bool* neg) {
     return e;
 }
 
-// Arrange the clauses of one level into slots, 8 per quarter-warp, minimising bank-group
-// conflicts (row index mod 8) per literal position.  Greedy: fill each octet from the pool,
-// trying the 6 literal permutations of each candidate; leftovers go in as they are.
+// Arrange the clauses of one level into slots, 8 per quarter-warp (one 128-byte shared-memory
+// wavefront of 16-byte rows), so that the 8 lanes hit 8 distinct bank groups (row index mod 8) in
+// each literal position wherever possible.  Literal positions inside a clause may be permuted
+// (the arithmetic is symmetric in the literals when the variables are distinct).
+// Best-fit over ALL octets of the level: each clause goes to the first octet — and literal
+// permutation — where it adds no conflict; clauses that fit nowhere are placed afterwards where
+// they cost least.  Returns through `wavefront_sum / wavefront_cnt` the average wavefronts per
+// quarter-warp access.
 inline void pack_level(const odesat_formula& f, const std::vector<int32_t>& clauses, std::vector<int32_t>& out_perm,
                        std::vector<uint64_t>& out_entry, double& wavefront_sum, int64_t& wavefront_cnt) {
     static const int P[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
     const size_t n = clauses.size();
-    std::vector<uint8_t> used(n, 0);
-    size_t remaining = n, scan_from = 0;
-    while (remaining > 0) {
-        // one octet
-        uint8_t mask[3] = {0, 0, 0};   // bank groups taken per literal position
-        int filled = 0;
-        int cnt[3][8] = {};
-        const size_t window = 512;     // bounded look-ahead keeps this O(M · window)
-        size_t looked = 0;
-        while (scan_from < n && used[scan_from]) ++scan_from;
-        for (size_t i = scan_from; i < n && filled < 8 && looked < window; ++i) {
-            if (used[i]) continue;
-            ++looked;
-            const int m = clauses[i];
-            int32_t var[3];
-            bool neg[3];
-            for (int j = 0; j < 3; ++j) {
-                const int32_t l = f.h_lits[f.h_off[m] + j];
-                var[j] = (l < 0 ? -l : l) - 1;
-                neg[j] = l < 0;
-            }
-            for (int p = 0; p < 6; ++p) {
-                const int b0 = var[P[p][0]] & 7, b1 = var[P[p][1]] & 7, b2 = var[P[p][2]] & 7;
-                if (!((mask[0] >> b0) & 1) && !((mask[1] >> b1) & 1) && !((mask[2] >> b2) & 1)) {
-                    mask[0] |= 1 << b0; mask[1] |= 1 << b1; mask[2] |= 1 << b2;
-                    cnt[0][b0]++; cnt[1][b1]++; cnt[2][b2]++;
-                    int32_t pv[3] = {var[P[p][0]], var[P[p][1]], var[P[p][2]]};
-                    bool pn[3] = {neg[P[p][0]], neg[P[p][1]], neg[P[p][2]]};
-                    out_perm.push_back(m);
-                    out_entry.push_back(pack_entry3(pv, pn));
-                    used[i] = 1;
-                    --remaining;
-                    ++filled;
-                    break;
+    // Slack: the level is rounded up to whole warps anyway (idle lanes cost nothing), so the
+    // spare slots become holes the packer may leave wherever an octet cannot be completed.
+    const size_t nb = ((n + 31) / 32 * 32) / 8;
+    struct Cl { int32_t m; int32_t var[3]; bool neg[3]; };
+    struct Bin { uint8_t mask[3] = {0, 0, 0}; uint8_t cnt[3][8] = {}; int filled = 0; Cl slot[8]; int cap = 8; };
+    std::vector<Bin> bins(nb);
+    auto load = [&](int32_t m) {
+        Cl c;
+        c.m = m;
+        for (int j = 0; j < 3; ++j) {
+            const int32_t l = f.h_lits[f.h_off[m] + j];
+            c.var[j] = (l < 0 ? -l : l) - 1;
+            c.neg[j] = l < 0;
+        }
+        return c;
+    };
+    auto place = [&](Bin& b, const Cl& c, int p) {
+        Cl q;
+        q.m = c.m;
+        for (int j = 0; j < 3; ++j) { q.var[j] = c.var[P[p][j]]; q.neg[j] = c.neg[P[p][j]]; }
+        for (int j = 0; j < 3; ++j) { b.mask[j] |= (uint8_t)(1u << (q.var[j] & 7)); b.cnt[j][q.var[j] & 7]++; }
+        b.slot[b.filled++] = q;
+    };
+    std::vector<Cl> leftover;
+    size_t first_open = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const Cl c = load(clauses[i]);
+        bool done = false;
+        while (first_open < nb && bins[first_open].filled >= bins[first_open].cap) ++first_open;
+        for (size_t bi = first_open; bi < nb && !done; ++bi) {
+            Bin& b = bins[bi];
+            if (b.filled >= b.cap) continue;
+            for (int p = 0; p < 6 && !done; ++p) {
+                const int b0 = c.var[P[p][0]] & 7, b1 = c.var[P[p][1]] & 7, b2 = c.var[P[p][2]] & 7;
+                if (!((b.mask[0] >> b0) & 1) && !((b.mask[1] >> b1) & 1) && !((b.mask[2] >> b2) & 1)) {
+                    place(b, c, p);
+                    done = true;
                 }
             }
         }
-        // top the octet up with whatever is left (conflicts accepted)
-        for (size_t i = scan_from; i < n && filled < 8 && remaining > 0; ++i) {
-            if (used[i]) continue;
-            const int m = clauses[i];
-            int32_t var[3];
-            bool neg[3];
-            for (int j = 0; j < 3; ++j) {
-                const int32_t l = f.h_lits[f.h_off[m] + j];
-                var[j] = (l < 0 ? -l : l) - 1;
-                neg[j] = l < 0;
-                cnt[j][var[j] & 7]++;
+        if (!done) leftover.push_back(c);
+    }
+    for (const Cl& c : leftover) {   // cheapest (octet, permutation) by added wavefronts
+        int best_cost = 1 << 30, best_p = 0;
+        size_t best_b = 0;
+        for (size_t bi = 0; bi < nb; ++bi) {
+            Bin& b = bins[bi];
+            if (b.filled >= b.cap) continue;
+            for (int p = 0; p < 6; ++p) {
+                int cost = 0;
+                for (int j = 0; j < 3; ++j) {
+                    const int r = c.var[P[p][j]] & 7;
+                    int mx = 0;
+                    for (int k = 0; k < 8; ++k) mx = std::max<int>(mx, b.cnt[j][k]);
+                    if (b.cnt[j][r] + 1 > mx) cost += 1;
+                }
+                if (cost < best_cost) { best_cost = cost; best_b = bi; best_p = p; }
             }
-            out_perm.push_back(m);
-            out_entry.push_back(pack_entry3(var, neg));
-            used[i] = 1;
-            --remaining;
-            ++filled;
         }
-        for (int j = 0; j < 3; ++j) {
-            int mx = 0;
-            for (int b = 0; b < 8; ++b) mx = std::max(mx, cnt[j][b]);
-            wavefront_sum += mx;
-            ++wavefront_cnt;
+        place(bins[best_b], c, best_p);
+    }
+    size_t last_used = 0;
+    for (size_t bi = 0; bi < nb; ++bi) if (bins[bi].filled) last_used = bi;
+    for (size_t bi = 0; bi <= last_used && n > 0; ++bi) {
+        const Bin& b = bins[bi];
+        for (int k = 0; k < 8; ++k) {
+            if (k < b.filled) {
+                out_perm.push_back(b.slot[k].m);
+                out_entry.push_back(pack_entry3(b.slot[k].var, b.slot[k].neg));
+            } else {          // hole: entry without the VALID bit, the thread idles
+                out_perm.push_back(-1);
+                out_entry.push_back(0);
+            }
         }
-        // pad a partial octet only at the very end of the level (caller pads to 32)
-        if (remaining == 0) break;
+        if (b.filled) {
+            for (int j = 0; j < 3; ++j) {
+                int mx = 0;
+                for (int k = 0; k < 8; ++k) mx = std::max<int>(mx, b.cnt[j][k]);
+                wavefront_sum += mx;
+                ++wavefront_cnt;
+            }
+        }
     }
 }
 
@@ -162,7 +186,11 @@ inline std::shared_ptr<TileLevels> build_tile_levels(const odesat_formula& f, in
         // target: levels of 1024 clauses (a whole number of 512-thread items), but never fewer
         // colours than the max variable degree; classes are capped at a multiple of 512
         int C = (int)std::max<int64_t>(f.max_degree + 2, (M + 1023) / 1024);
-        const int cap = (int)(((M + C - 1) / C + 511) / 512 * 512);
+        int cap = (int)(((M + C - 1) / C + 511) / 512 * 512);
+        if (cap >= 512) {   // leave one warp of slack per level for the bank-conflict packer's holes
+            cap -= 32;
+            C = (int)std::max<int64_t>(C, (M + cap - 1) / cap);
+        }
         std::vector<std::vector<uint64_t>> usedc;   // per variable: bitset of colours taken
         int words = (C + 63 + 64) / 64;             // slack for overflow colours
         std::vector<uint64_t> bits((size_t)N * words, 0);
@@ -206,7 +234,8 @@ inline std::shared_ptr<TileLevels> build_tile_levels(const odesat_formula& f, in
 // `depth`: prefetch ring depth of the kernel the schedule is for; the item list is padded with
 // empty items to a multiple of it (and to more than one ring) so that item i always lives in
 // ring slot i % depth and a slot is stored before it is prefetched again.
-inline std::shared_ptr<TileSchedule> build_tile_schedule(const odesat_formula& f, const TileLevels& lv, int kind, int nt, int depth) {
+inline std::shared_ptr<TileSchedule> build_tile_schedule(const odesat_formula& f, const TileLevels& lv, int kind, int nt, int depth,
+                                                         bool upload = true) {
     auto s = std::make_shared<TileSchedule>();
     s->kind = kind;
     s->nt = nt;
@@ -217,19 +246,20 @@ inline std::shared_ptr<TileSchedule> build_tile_schedule(const odesat_formula& f
         if (b.empty()) continue;
         const size_t base0 = s->perm.size();
         pack_level(f, b, s->perm, s->entry, wsum, wcnt);
-        const size_t n = s->perm.size() - base0;
-        while (s->perm.size() % 8) { s->perm.push_back(-1); s->entry.push_back(0); }
+        const size_t n = s->perm.size() - base0;   // slots of the level incl. holes: a multiple of 8
         for (size_t o = 0; o < n; o += (size_t)nt) {
             const size_t cnt = std::min<size_t>((size_t)nt, n - o);
             s->items.push_back(pack_item((uint32_t)(base0 + o), (uint32_t)cnt, o + (size_t)nt >= n));
         }
         ++s->nlev;
     }
-    while (s->items.size() % (size_t)depth || s->items.size() <= (size_t)depth) s->items.push_back(pack_item(0, 0, false));
+    const size_t pad = (size_t)((depth % 2) ? 2 * depth : depth);   // the strict first-step kernel uses a ring of 2
+    while (s->items.size() % pad || s->items.size() <= (size_t)depth) s->items.push_back(pack_item(0, 0, false));
     s->Mpad = (int64_t)s->perm.size();
     if (s->Mpad >= (1 << 20)) throw Error(ODESAT_EUNSUPPORTED, "tile schedule: more than 2^20 clause slots");
     s->n_items = (int)s->items.size();
     s->conflict_wavefronts = wcnt ? wsum / wcnt : 1.0;
+    if (!upload) return s;
     s->d_items.alloc(std::max<size_t>(s->items.size(), 1));
     s->d_perm.alloc(std::max<size_t>(s->perm.size(), 1));
     s->d_entry.alloc(std::max<size_t>(s->entry.size(), 1));

@@ -1,0 +1,93 @@
+"""Host-side schedule compiler of the TILE engine (no GPU needed): the level structure must make
+the shared-memory read-modify-write race-free, and the EXACT schedule must preserve the
+reference's per-variable summation order (system.rs:35-80)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from odesat_b200 import _lib as L
+from odesat_b200 import cnf
+
+
+def compile_schedule(f, sched, threads, depth):
+    out = np.zeros(4, np.int64)
+    perm = np.full(f.n_clauses * 2 + 4096, -7, np.int32)
+    items = np.zeros(f.n_clauses + 4096, np.uint32)
+    P = C.c_void_p
+    L.check(L.lib().odesat_tile_schedule_stats(
+        f.varnum, f.n_clauses, f.clause_off.ctypes.data_as(P), f.lits.ctypes.data_as(P), sched, threads, depth,
+        perm.ctypes.data_as(P), len(perm), items.ctypes.data_as(P), len(items), out.ctypes.data_as(P)))
+    nlev, n_items, slots, wf = (int(x) for x in out)
+    return nlev, items[:n_items], perm[:slots], wf / 1000.0
+
+
+def levels_of(items, perm):
+    """→ list of levels, each the list of clause indices it processes (holes dropped)."""
+    levels, cur = [], []
+    for it in items:
+        base, cnt, last = int(it) & 0xFFFFF, (int(it) >> 20) & 0x7FF, bool(int(it) >> 31)
+        cur.extend(int(m) for m in perm[base:base + cnt] if m >= 0)
+        if last:
+            levels.append(cur)
+            cur = []
+    assert not cur
+    return levels
+
+
+@pytest.mark.parametrize("sched", [L.SCHED_EXACT, L.SCHED_BALANCED])
+@pytest.mark.parametrize("threads,depth", [(128, 4), (512, 5), (1024, 4), (512, 3)])
+def test_schedule_invariants(sched, threads, depth):
+    f = cnf.random_ksat(2000, 4.3, seed=5)
+    var = (np.abs(f.lits) - 1).reshape(-1, 3)
+    nlev, items, perm, wf = compile_schedule(f, sched, threads, depth)
+    # every clause exactly once; padding only as holes
+    assert sorted(perm[perm >= 0]) == list(range(f.n_clauses))
+    # ring invariants of the kernel: item i lives in ring slot i % depth in every step, and a slot
+    # is stored before it is prefetched again; the strict first-step kernel uses a ring of 2
+    assert len(items) % depth == 0 and len(items) % 2 == 0 and len(items) > depth
+    # items tile the slot array in order, never wider than the CTA
+    pos = 0
+    for it in items:
+        base, cnt = int(it) & 0xFFFFF, (int(it) >> 20) & 0x7FF
+        if cnt == 0:
+            continue
+        assert base == pos and cnt <= threads and base % 8 == 0
+        pos = base + cnt
+    assert pos == len(perm)
+    levels = levels_of(items, perm)
+    assert len(levels) == nlev
+    # race freedom: no variable twice inside a level
+    level_of = np.empty(f.n_clauses, np.int64)
+    for li, lv in enumerate(levels):
+        vs = var[lv].reshape(-1)
+        assert len(np.unique(vs)) == len(vs)
+        level_of[lv] = li
+    if sched == L.SCHED_EXACT:
+        # order preservation: each variable meets its clauses in ascending clause index
+        for i in range(f.varnum):
+            occ = np.flatnonzero((var == i).any(axis=1))
+            assert (np.diff(level_of[occ]) > 0).all()
+    else:
+        sizes = np.array([len(lv) for lv in levels])
+        assert sizes.max() - np.median(sizes) <= 64            # balanced classes
+    assert 1.0 <= wf < 1.35                                      # bank-conflict packing quality
+
+
+def test_schedule_is_deterministic_and_rejects_unsupported():
+    f = cnf.random_ksat(500, 4.3, seed=1)
+    a = compile_schedule(f, L.SCHED_BALANCED, 512, 4)
+    b = compile_schedule(f, L.SCHED_BALANCED, 512, 4)
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    g = cnf.random_ksat(100, 5.0, seed=1, k=4)
+    with pytest.raises(L.OdesatError):
+        compile_schedule(g, L.SCHED_EXACT, 512, 4)
+    dup = cnf.Formula(3, np.array([0, 3], np.int64), np.array([1, 1, -2], np.int32), {})
+    with pytest.raises(L.OdesatError):
+        compile_schedule(dup, L.SCHED_EXACT, 128, 2)
+
+
+def test_aim_fixture_schedule(golden_dir):
+    f = cnf.load_dimacs(str(golden_dir / "aim100_sat.cnf"))
+    nlev, items, perm, wf = compile_schedule(f, L.SCHED_EXACT, 128, 6)
+    assert nlev >= 8 and sorted(perm[perm >= 0]) == list(range(160))
