@@ -321,7 +321,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     import __graft_entry__ as g
-    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0 and os.environ.get("ODESAT_SKIP_BUILD") != "1":
         g.build()
     if args.impl == "reference":
         run_reference(args)

@@ -11,7 +11,7 @@ import subprocess
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-SO_PATH = _HERE / "csrc" / "libodesat_b200.so"
+SO_PATH = Path(os.environ.get("ODESAT_B200_SO", str(_HERE / "csrc" / "libodesat_b200.so")))   # override: tuning builds only
 
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, 1, 2, 3, 4
 F64, F32 = 0, 1

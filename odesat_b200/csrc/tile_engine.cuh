@@ -144,16 +144,6 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
-// Full 16-byte row store.  Written as volatile asm so that the compiler cannot shrink it to an
-// 8-byte store of the dv half: 16 lanes × 8 B at stride 16 is an unavoidable 2-way bank
-// conflict, whereas the 128-bit store is served per quarter-warp and is conflict-free whenever
-// the octet's rows are distinct mod 8 (what the schedule packer arranges).
-__device__ __forceinline__ void st_row(float4* p, const float4& r) {
-    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"((unsigned)__cvta_generic_to_shared(p)), "f"(r.x), "f"(r.y), "f"(r.z), "f"(r.w) : "memory");
-}
-__device__ __forceinline__ void st_row(double2* p, const double2& r) {
-    asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"((unsigned)__cvta_generic_to_shared(p)), "d"(r.x), "d"(r.y) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -250,7 +240,7 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
                 cp_async_wait<D - 1>();                     // this thread's cell of item i has landed
                 const bool mine = tid < ((it >> 20) & 0x7FFu);
                 if (ER && mine) e = my_cell_e[k * NT];
-                if (mine && (e.y & (unsigned)(TILE_VALID_BIT >> 32))) {
+                if (mine) {
                     const Mem mm = my_cell_m[k * NT];
                     const unsigned i0 = e.x & 0xFFFFu, i1 = e.x >> 16, i2 = e.y & 0xFFFFu;
                     const unsigned neg[3] = {(e.y >> 16) & 1u, (e.y >> 17) & 1u, (e.y >> 18) & 1u};
@@ -267,9 +257,11 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
                         d[0][w] = dd[0]; d[1][w] = dd[1]; d[2][w] = dd[2];
                     }
                     // full-row stores: an 8-byte store of the dv half alone is a 2-way bank conflict
-                    st_row(rows + i0, IO::pack(v[0], d[0]));
-                    st_row(rows + i1, IO::pack(v[1], d[1]));
-                    st_row(rows + i2, IO::pack(v[2], d[2]));
+                    // only the dv half changes; measured on B200, the 8-byte store (with its 2-way bank
+                    // conflict across the two octets of a half-warp) beats rewriting the full row
+                    IO::store_dv(rows + i0, d[0]);
+                    IO::store_dv(rows + i1, d[1]);
+                    IO::store_dv(rows + i2, d[2]);
                     __stcg(my_mem + (it & 0xFFFFFu), IO::pack_mem(xs, xl));
                 }
                 {   // refill cell k with item i + D (next step's item i + D − n_items at the end)
