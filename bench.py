@@ -111,11 +111,14 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def traffic_for(engine_name, precision):
+def traffic_for(engine_name, precision, schedule, steps, launches):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu
+    capture (profiles/traffic.json, bytes per Euler step), scaled to one launch of this run."""
     p = ROOT / "profiles" / "traffic.json"
     if p.exists():
         try:
-            return json.loads(p.read_text()).get(f"{engine_name}_{precision}")
+            per_step = json.loads(p.read_text()).get(f"{engine_name}_{precision}_{schedule}")
+            return None if per_step is None else per_step * steps / max(launches, 1)
         except Exception:
             return None
     return None
@@ -228,6 +231,17 @@ def run_gpu(args):
     st, _ = b.status()
     flagged = int((st >= 0).sum())
     b.close()
+    other = None
+    if not args.quick and eng_name == "tile":
+        # the same K steps with the other clause schedule, for the record (not the headline value)
+        osched = L.SCHED_EXACT if sched == L.SCHED_BALANCED else L.SCHED_BALANCED
+        ob = B.ReplicaBatch(F, R, prec, engine, osched)
+        ob.init(RUN_SEED, rank * R)
+        ob.run_fixed(DT, zeta, args.warmup, freeze=False)
+        oms = ob.run_fixed(DT, zeta, args.steps, freeze=False, timed=True)
+        ob.close()
+        other = {"schedule": "exact" if osched == L.SCHED_EXACT else "balanced", "ms_per_step": oms / args.steps,
+                 "roofline_frac": bytes_step * args.steps / (oms * 1e-3) / 1e9 / peak}
 
     if args.quick:
         if rank == 0:
@@ -285,7 +299,7 @@ def run_gpu(args):
                        "M": f.n_clauses, "engine": eng_name, "schedule": args.schedule, "formula_seed": FORMULA_SEED,
                        "parallelism": f"replica-sharded x{world}, no data-path collective",
                        "l2": f"state {bytes_step / 2 / 1e6:.0f} MB per GPU is larger than L2 (126 MB); no flush needed",
-                       "flagged_replicas": flagged,
+                       "flagged_replicas": flagged, "other_schedule_same_run": other,
                        "e2e_call": f"one odesat_simulate_batch call of {e2e_steps} steps per GPU: pinned host states "
                                    "in, per-replica flags + exact verification + winner assignment out"},
             "clocks": clk.summary(),
@@ -293,8 +307,10 @@ def run_gpu(args):
                     "d2h_bytes_per_step": d2h / e2e_steps, "seconds_per_call": float(te.item())},
             "gpu_launches": n_launch,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic_for(eng_name, args.precision), "peak_source": peak_src,
-                         "algorithmic_bytes_per_step": bytes_step, "launches": n_launch,
+                         "traffic": traffic_for(eng_name, args.precision, args.schedule, args.steps, n_launch),
+                         "peak_source": peak_src,
+                         "algorithmic_bytes_per_step": bytes_step,
+                         "algorithmic_bytes_per_launch": bytes_step * args.steps / max(n_launch, 1), "launches": n_launch,
                          "avg_launch_ms": ms / max(n_launch, 1), "frac_of_8TBs": achieved / 8000.0},
         }
         if cpu_val is not None:
@@ -316,7 +332,9 @@ def main():
     ap.add_argument("--replicas", type=int, default=4096, help="replicas per GPU")
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--engine", default="auto", choices=["auto", "gather", "tile"])
-    ap.add_argument("--schedule", default="exact", choices=["exact", "balanced"])
+    ap.add_argument("--schedule", default="balanced", choices=["exact", "balanced"],
+                    help="tile-engine clause schedule: balanced = throughput mode (dv summed in colour order, "
+                         "agrees with the reference to rounding); exact = the reference's summation order, bit-identical")
     ap.add_argument("--quick", action="store_true", help="tuning aid: device-resident timing only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

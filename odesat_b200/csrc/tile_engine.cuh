@@ -90,7 +90,7 @@ __device__ __forceinline__ double fma_exact(double a, double b, double c) { retu
 //             · the rigidity term dropped: it is ±0 and x + (±0) = x for every x the running
 //               sum can hold
 template <typename T, bool STRICT>
-__device__ __forceinline__ void clause_math(const T (&v)[3], T (&d)[3], const unsigned (&neg)[3], T& xs, T& xl, bool frozen,
+__device__ __forceinline__ void clause_math(const T (&v)[3], T (&d)[3], const T (&q)[3], T& xs, T& xl, bool frozen,
                                             bool& unsat, T dt, T zeta, T xl_max) {
     const T hi_s = T(1) - Kc<T>::EPSILON;
     T a[3], mn, sm;
@@ -99,13 +99,12 @@ __device__ __forceinline__ void clause_math(const T (&v)[3], T (&d)[3], const un
         sm = inf_v<T>();
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            const T q = neg[j] ? T(-1) : T(1);
-            a[j] = T(1) - q * v[j];                                         // :49
+            a[j] = T(1) - q[j] * v[j];                                      // :49
             if (a[j] < mn) { sm = mn; mn = a[j]; } else if (a[j] < sm) { sm = a[j]; }   // :50-55
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) a[j] = fma_exact(neg[j] ? T(1) : T(-1), v[j], T(1));
+        for (int j = 0; j < 3; ++j) a[j] = fma_exact(-q[j], v[j], T(1));
         const T lo = rmin(a[0], a[1]), hi = rmax(a[0], a[1]);
         mn = rmin(lo, a[2]);
         sm = rmax(lo, rmin(hi, a[2]));
@@ -116,22 +115,29 @@ __device__ __forceinline__ void clause_math(const T (&v)[3], T (&d)[3], const un
         const T rg = (T(1) + zeta * xl) * (T(1) - xs);
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            const T q = neg[j] ? T(-1) : T(1);
-            const T g = (T(0.5) * q) * ((a[j] != mn) ? mn : sm);            // :64-70
-            const T r = (cm == a[j]) ? T(0.5) * (q - v[j]) : T(0);          // :73-77
+            const T g = (T(0.5) * q[j]) * ((a[j] != mn) ? mn : sm);         // :64-70
+            const T r = (cm == a[j]) ? T(0.5) * (q[j] - v[j]) : T(0);       // :73-77
             d[j] = d[j] + (wgt * g + rg * r);                               // :80
         }
     } else {
+        // d + q·(h·sel): q = ±1 makes the product exact, so the FMA rounds exactly like d + (±x)
         const T h = T(0.5) * wgt;
 #pragma unroll
-        for (int j = 0; j < 3; ++j) d[j] = d[j] + flip_sign(h * ((a[j] != mn) ? mn : sm), neg[j]);
+        for (int j = 0; j < 3; ++j) d[j] = fma_exact(h * ((a[j] != mn) ? mn : sm), q[j], d[j]);
     }
     const T dxs = (Kc<T>::BETA * (xs + Kc<T>::EPSILON)) * (cm - Kc<T>::GAMMA);   // :84
     const T dxl = Kc<T>::ALPHA * (cm - Kc<T>::DELTA);                            // :85
     unsat = unsat || !(cm < Kc<T>::GAMMA);                                       // :88
-    if (!frozen) {
-        xs = euler_clamp(xs, dxs, dt, Kc<T>::EPSILON, hi_s);                     // :94
-        xl = euler_clamp(xl, dxl, dt, T(1), xl_max);                             // :95
+    if (STRICT) {
+        if (!frozen) {
+            xs = euler_clamp(xs, dxs, dt, Kc<T>::EPSILON, hi_s);                 // :94
+            xl = euler_clamp(xl, dxl, dt, T(1), xl_max);                         // :95
+        }
+    } else {
+        // a frozen replica is integrated with dt = 0: its memories are finite and already inside
+        // their clamp ranges, so y + 0·dy = y exactly and the clamps are the identity
+        xs = euler_clamp(xs, dxs, dt, Kc<T>::EPSILON, hi_s);
+        xl = euler_clamp(xl, dxl, dt, T(1), xl_max);
     }
 }
 
@@ -143,6 +149,17 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+// base + idx·16 / base + idx·8 as one IMAD.WIDE (FMA pipe) instead of a 4-instruction ALU sequence
+template <typename P> __device__ __forceinline__ P* at16(P* base, unsigned idx) {
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(r) : "r"(idx), "l"((unsigned long long)base));
+    return (P*)r;
+}
+template <typename P> __device__ __forceinline__ P* at8(P* base, unsigned idx) {
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, 8, %2;" : "=l"(r) : "r"(idx), "l"((unsigned long long)base));
+    return (P*)r;
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -177,7 +194,7 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
     Row* rows = reinterpret_cast<Row*>(smem_raw);
     Mem* ring_m = reinterpret_cast<Mem*>(smem_raw + (size_t)a.N * sizeof(Row));
     uint2* ring_e = reinterpret_cast<uint2*>(ring_m + D * NT);
-    uint32_t* s_items = reinterpret_cast<uint32_t*>(ring_e + (ER ? D * NT : 0));
+    uint2* s_items = reinterpret_cast<uint2*>(ring_e + (ER ? D * NT : 0));   // {slot base, count | last << 31}
 
     const unsigned tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
@@ -188,7 +205,10 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
     uint2* my_cell_e = ring_e + tid;
     const int n_items = a.n_items;
 
-    for (int i = tid; i < n_items; i += NT) s_items[i] = a.items[i];
+    for (int i = tid; i < n_items; i += NT) {
+        const uint32_t it = a.items[i];
+        s_items[i] = make_uint2(it & 0xFFFFFu, ((it >> 20) & 0x7FFu) | (it & TILE_ITEM_LAST));
+    }
     for (int i = tid; i < a.N; i += NT) {
         T v[W], dv[W];
 #pragma unroll
@@ -206,16 +226,16 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-        const uint32_t it = s_items[k];
-        if (tid < ((it >> 20) & 0x7FFu)) {
-            cp_async16(my_cell_m + k * NT, my_mem + (it & 0xFFFFFu));
-            if (ER) cp_async8(my_cell_e + k * NT, my_entry + (it & 0xFFFFFu));
+        const uint2 it = s_items[k];
+        if (tid < (it.y & 0x7FFFFFFFu)) {
+            cp_async16(my_cell_m + k * NT, at16(my_mem, it.x));
+            if (ER) cp_async8(my_cell_e + k * NT, at8(my_entry, it.x));
         }
         cp_async_commit();
     }
-    uint32_t it_next = s_items[0];
+    uint2 it_next = s_items[0];
     uint2 e_next = make_uint2(0u, 0u);
-    if (!ER && tid < ((it_next >> 20) & 0x7FFu)) e_next = __ldg(my_entry + (it_next & 0xFFFFFu));
+    if (!ER && tid < (it_next.y & 0x7FFFFFFFu)) e_next = __ldg(at8(my_entry, it_next.x));
 
     for (int s = 0; s < a.nsteps; ++s) {
         bool all_frozen = true;
@@ -223,27 +243,28 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
         for (int w = 0; w < W; ++w) all_frozen = all_frozen && frozen[w];
         if (all_frozen) break;
         bool unsat[W];
+        T dtw[W];   // per-replica step: 0 freezes a replica without a branch (fast path only)
 #pragma unroll
-        for (int w = 0; w < W; ++w) unsat[w] = false;
+        for (int w = 0; w < W; ++w) { unsat[w] = false; dtw[w] = (!STRICT && frozen[w]) ? T(0) : a.dt; }
         // ------------------------------ clause phase -----------------------------------
         for (int base = 0; base < n_items; base += D) {
 #pragma unroll
             for (int k = 0; k < D; ++k) {
                 const int i = base + k;
-                const uint32_t it = it_next;
+                const uint2 it = it_next;
                 uint2 e = e_next;
                 {   // descriptor (and, without ER, packed clause) of the NEXT item, wrapping into the next step
                     const int i1 = (i + 1 == n_items) ? 0 : i + 1;
                     it_next = s_items[i1];
-                    if (!ER && tid < ((it_next >> 20) & 0x7FFu)) e_next = __ldg(my_entry + (it_next & 0xFFFFFu));
+                    if (!ER && tid < (it_next.y & 0x7FFFFFFFu)) e_next = __ldg(at8(my_entry, it_next.x));
                 }
                 cp_async_wait<D - 1>();                     // this thread's cell of item i has landed
-                const bool mine = tid < ((it >> 20) & 0x7FFu);
+                const bool mine = tid < (it.y & 0x7FFFFFFFu);
                 if (ER && mine) e = my_cell_e[k * NT];
                 if (mine) {
                     const Mem mm = my_cell_m[k * NT];
                     const unsigned i0 = e.x & 0xFFFFu, i1 = e.x >> 16, i2 = e.y & 0xFFFFu;
-                    const unsigned neg[3] = {(e.y >> 16) & 1u, (e.y >> 17) & 1u, (e.y >> 18) & 1u};
+                    const T q[3] = {(e.y >> 16) & 1u ? T(-1) : T(1), (e.y >> 17) & 1u ? T(-1) : T(1), (e.y >> 18) & 1u ? T(-1) : T(1)};
                     T v[3][W], d[3][W], xs[W], xl[W];
                     IO::unpack(rows[i0], v[0], d[0]);
                     IO::unpack(rows[i1], v[1], d[1]);
@@ -253,28 +274,27 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
                     for (int w = 0; w < W; ++w) {
                         const T vv[3] = {v[0][w], v[1][w], v[2][w]};
                         T dd[3] = {d[0][w], d[1][w], d[2][w]};
-                        clause_math<T, STRICT>(vv, dd, neg, xs[w], xl[w], frozen[w], unsat[w], a.dt, a.zeta, a.xl_max);
+                        clause_math<T, STRICT>(vv, dd, q, xs[w], xl[w], frozen[w], unsat[w], dtw[w], a.zeta, a.xl_max);
                         d[0][w] = dd[0]; d[1][w] = dd[1]; d[2][w] = dd[2];
                     }
-                    // full-row stores: an 8-byte store of the dv half alone is a 2-way bank conflict
                     // only the dv half changes; measured on B200, the 8-byte store (with its 2-way bank
                     // conflict across the two octets of a half-warp) beats rewriting the full row
                     IO::store_dv(rows + i0, d[0]);
                     IO::store_dv(rows + i1, d[1]);
                     IO::store_dv(rows + i2, d[2]);
-                    __stcg(my_mem + (it & 0xFFFFFu), IO::pack_mem(xs, xl));
+                    __stcg(at16(my_mem, it.x), IO::pack_mem(xs, xl));
                 }
                 {   // refill cell k with item i + D (next step's item i + D − n_items at the end)
                     int nx = i + D;
                     if (nx >= n_items) nx -= n_items;
-                    const uint32_t itn = s_items[nx];
-                    if (tid < ((itn >> 20) & 0x7FFu)) {
-                        cp_async16(my_cell_m + k * NT, my_mem + (itn & 0xFFFFFu));
-                        if (ER) cp_async8(my_cell_e + k * NT, my_entry + (itn & 0xFFFFFu));
+                    const uint2 itn = s_items[nx];
+                    if (tid < (itn.y & 0x7FFFFFFFu)) {
+                        cp_async16(my_cell_m + k * NT, at16(my_mem, itn.x));
+                        if (ER) cp_async8(my_cell_e + k * NT, at8(my_entry, itn.x));
                     }
                     cp_async_commit();
                 }
-                if (it & TILE_ITEM_LAST) __syncthreads();   // end of a level: block-uniform
+                if ((int)it.y < 0) __syncthreads();         // last item of a level: block-uniform
             }
         }
         // ------------------------------ flags + variable phase ---------------------------
@@ -286,7 +306,8 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
             IO::unpack(rows[i], v, dv);
 #pragma unroll
             for (int w = 0; w < W; ++w) {
-                if (!frozen[w]) v[w] = euler_clamp(v[w], dv[w], a.dt, T(-1), T(1));              // :96
+                if (STRICT) { if (!frozen[w]) v[w] = euler_clamp(v[w], dv[w], a.dt, T(-1), T(1)); }   // :96
+                else v[w] = euler_clamp(v[w], dv[w], dtw[w], T(-1), T(1));
                 dv[w] = T(0);
             }
             rows[i] = IO::pack(v, dv);
@@ -396,7 +417,7 @@ template <typename T> struct TileEngine {
 
     static bool entry_in_ring(int nt) { return nt < 1024; }
     static size_t smem_bytes(int64_t N, int n_items, int nt, int depth) {
-        return (size_t)N * 16 + (size_t)nt * depth * (entry_in_ring(nt) ? 24 : 16) + (size_t)(n_items + 2) * 4;
+        return (size_t)N * 16 + (size_t)nt * depth * (entry_in_ring(nt) ? 24 : 16) + (size_t)(n_items + 2) * 8;
     }
     // deepest ring (≤ 6) that fits beside the variable rows
     static int pick_depth(int64_t N, int nt, int n_items_guess) {
@@ -420,13 +441,19 @@ template <typename T> struct TileEngine {
         tiles = (R + W - 1) / W;
         auto lv = f.tile_levels.find(kind);
         if (lv == f.tile_levels.end()) lv = f.tile_levels.emplace(kind, build_tile_levels(f, kind)).first;
-        // CTA width: wide enough that a typical level is one item; small formulas get a narrow CTA
-        std::vector<size_t> sizes;
-        for (const auto& b : lv->second->bucket) if (!b.empty()) sizes.push_back(b.size());
-        std::sort(sizes.begin(), sizes.end());
-        const size_t median = sizes.empty() ? 0 : sizes[sizes.size() / 2];
-        nt = median > 640 ? 1024 : (median > 128 ? 512 : 128);
-        static const int cand[] = {128, 512, 1024};
+        // CTA width: measured on B200 the step time is ≈ items(nt) · (454 + nt) — every item pays a
+        // fixed latency/barrier cost plus an issue cost proportional to the CTA width — so pick the
+        // instantiated width that minimises it for this formula's level sizes.
+        {
+            double best = 1e300;
+            for (int c : {128, 512, 640, 768, 1024}) {
+                double items = 0;
+                for (const auto& b : lv->second->bucket) items += (double)((b.size() + c - 1) / c);
+                const double cost = items * (454.0 + c);
+                if (cost < best) { best = cost; nt = c; }
+            }
+        }
+        static const int cand[] = {128, 512, 640, 768, 1024};
         if (const char* e = std::getenv("ODESAT_TILE_NT")) {
             const int v = std::atoi(e);
             for (int c : cand) if (v == c) nt = v;
@@ -438,7 +465,7 @@ template <typename T> struct TileEngine {
             const int guess = (int)(f.M / nt + 3 * (int64_t)lv->second->bucket.size() + 16);
             depth = pick_depth(f.N, nt, guess);
             if (depth >= 2 || nt == 128) break;
-            nt = nt == 1024 ? 512 : 128;
+            nt = nt == 1024 ? 768 : (nt == 768 ? 640 : (nt == 640 ? 512 : 128));
         }
         if (depth < 2) throw Error(ODESAT_EUNSUPPORTED, "variables do not fit in shared memory");
         if (want >= 2 && want <= depth) depth = want;
@@ -503,6 +530,8 @@ template <typename T> struct TileEngine {
     void launch_nt(const TileArgs<T>& a, bool strict) {
         if (nt == 128) launch_d<128>(a, strict);
         else if (nt == 512) launch_d<512>(a, strict);
+        else if (nt == 640) launch_d<640>(a, strict);
+        else if (nt == 768) launch_d<768>(a, strict);
         else launch_d<1024>(a, strict);
     }
 

@@ -141,3 +141,21 @@ def test_full_size_baseline_config_engines_agree_and_match_oracle(prec):
     assert txl.min() >= 1 and txl.max() <= 1e4 * F.M
     for r in sample:
         assert bool(ver[r]) == f.evaluate(tv[r] > 0)
+
+
+def test_tile_balanced_f32_meets_north_star_tolerance():
+    """Throughput configuration (f32, BALANCED schedule): one RHS + Euler step on identical state
+    within 1e-5 relative of the f32 oracle (north star), memories bit-exact."""
+    f = cnf.random_ksat(3000, 4.3, seed=8)
+    D = S.DeviceFormula(f)
+    F = O.OracleFormula(f.varnum, f.clause_off, f.lits)
+    rng = np.random.default_rng(2)
+    R = 64
+    v, xs, xl = random_state(rng, F.N, F.M, np.float32, R=R)
+    b = B.ReplicaBatch(D, R, L.F32, L.ENGINE_TILE, L.SCHED_BALANCED)
+    b.upload(v, xs, xl)
+    b.run_fixed(0.01, 0.001, 1, freeze=False)
+    gv, gxs, gxl = b.download()
+    F.batch_fixed(v, xs, xl, 0.01, 0.001, 1, freeze=False)
+    np.testing.assert_allclose(gv, v, rtol=1e-5, atol=1e-6)
+    assert eq(gxs, xs) and eq(gxl, xl)
