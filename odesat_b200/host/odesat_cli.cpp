@@ -1,0 +1,155 @@
+// odesat_cli.cpp — `solve` / `batch` / `inter` driver over libodesat_b200 with the reference's
+// flags (-f -o -t -n -s -l -b, main.rs:31-141) and console lines (main.rs:156-200, 263-320,
+// 335-383).  SURVEY §8f row 1: the DIMACS reader, normaliser and result writer are restated here
+// (cnf.rs:138-219, 246-264, 289-315) so the GPU path is runnable end to end without the Rust crate.
+// Not restated: `-r` ratio preprocessing (cnf.rs:317-840) — `solve` integrates the un-preprocessed
+// formula — and `stoch`.  Extra flags: --seed (the reference's RNG is OS-seeded), --f32.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <set>
+#include <sstream>
+
+#include "system.hpp"
+
+using namespace odesat;
+
+// cnf.rs:138-172
+static CNFFormula parse_dimacs_format(const std::string& input, std::vector<std::vector<int>>& raw) {
+    CNFFormula f;
+    bool have = false;
+    std::istringstream in(input);
+    std::string line;
+    std::set<std::size_t> vars;
+    while (std::getline(in, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (!line.empty() && line[0] == 'c') continue;
+        if (line.rfind("p cnf", 0) == 0) {
+            std::istringstream ls(line);
+            std::string p, cnf;
+            ls >> p >> cnf >> f.varnum;
+            have = true;
+            continue;
+        }
+        std::istringstream ls(line);
+        std::string tok;
+        std::vector<int> lits;
+        while (ls >> tok) {
+            if (tok == "0") break;
+            lits.push_back(std::stoi(tok));
+        }
+        raw.push_back(lits);
+        for (int l : lits) vars.insert((std::size_t)std::abs(l));
+    }
+    if (!have) f.varnum = vars.size();
+    return f;
+}
+
+// cnf.rs:206-219 (ascending file name instead of HashSet order; varnum stays the header value)
+static std::map<std::size_t, std::size_t> normalize(const std::vector<std::vector<int>>& raw, CNFFormula& f) {
+    std::set<std::size_t> vars;
+    for (const auto& c : raw) for (int l : c) vars.insert((std::size_t)std::abs(l));
+    std::map<std::size_t, std::size_t> name_map;
+    for (std::size_t v : vars) { const std::size_t k = name_map.size(); name_map[v] = k; }
+    for (const auto& c : raw) {
+        CNFClause cl;
+        for (int l : c) cl.literals.push_back({name_map[(std::size_t)std::abs(l)], l < 0});
+        f.clauses.push_back(cl);
+    }
+    return name_map;
+}
+
+// cnf.rs:246-264 on the ORIGINAL formula
+static bool evaluate_cnf(const std::map<std::size_t, bool>& values, const std::vector<std::vector<int>>& raw) {
+    for (const auto& c : raw) {
+        bool sat = false;
+        for (int l : c) {
+            auto it = values.find((std::size_t)std::abs(l));
+            const bool val = it != values.end() && it->second;
+            sat = sat || (l < 0 ? !val : val);
+        }
+        if (!sat) return false;
+    }
+    return true;
+}
+
+static int usage() {
+    std::fprintf(stderr, "usage: odesat_b200_cli <solve|batch|inter> -f FILE [-o OUT] [-t TOL] [-n STEPS] [-s STEP] [-l ZETA] [-b BATCH] [--seed S] [--f32]\n");
+    return 2;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 2) return usage();
+    const std::string cmd = argv[1];
+    std::string input, output;
+    std::optional<double> tol, step, zeta;
+    std::optional<std::size_t> steps;
+    std::size_t batch = 0;
+    uint64_t seed = 1;
+    bool f32 = false;
+    for (int i = 2; i < argc; ++i) {
+        const std::string a = argv[i];
+        auto next = [&]() -> const char* { if (i + 1 >= argc) { usage(); std::exit(2); } return argv[++i]; };
+        if (a == "-f" || a == "--input") input = next();
+        else if (a == "-o" || a == "--output") output = next();
+        else if (a == "-t" || a == "--tolerance") tol = std::atof(next());
+        else if (a == "-n" || a == "--step-number") steps = (std::size_t)std::atoll(next());
+        else if (a == "-s" || a == "--step-size") step = std::atof(next());
+        else if (a == "-l" || a == "--learning-rate") zeta = std::atof(next());
+        else if (a == "-b" || a == "--batch-size") batch = (std::size_t)std::atoll(next());
+        else if (a == "--seed") seed = (uint64_t)std::atoll(next());
+        else if (a == "--f32") f32 = true;
+        else if (a == "-r" || a == "--ctv-ratio") { next(); std::fprintf(stderr, "note: -r preprocessing is out of scope; integrating the formula as given\n"); }
+        else return usage();
+    }
+    if (input.empty() || (cmd != "solve" && cmd != "batch" && cmd != "inter")) return usage();
+    if ((cmd == "batch" || cmd == "inter") && batch == 0) return usage();
+    if (cmd == "batch" && !steps) return usage();                       // main.rs:96-97: -n is required
+    try {
+        std::printf("Reading CNF formula from file...\n");
+        std::ifstream fh(input);
+        if (!fh) { std::perror(input.c_str()); return 1; }
+        std::stringstream ss;
+        ss << fh.rdbuf();
+        std::printf("Parsing CNF formula...\n");
+        std::vector<std::vector<int>> raw;
+        CNFFormula f = parse_dimacs_format(ss.str(), raw);
+        std::printf("Normalizing CNF formula...\n");
+        const auto name_map = normalize(raw, f);
+        system::Formula F(f);
+        std::printf("Simulating...\n");
+        odesat_params p = system::make_params(tol, step, steps, zeta);
+        p.precision = f32 ? ODESAT_F32 : ODESAT_F64;
+        const int64_t R = cmd == "solve" ? 1 : (int64_t)batch;
+        const int mode = cmd == "inter" ? ODESAT_MODE_INTER : ODESAT_MODE_BATCH;
+        if (cmd == "solve" && !steps) p.steps = 1 << 30;   // the reference loops forever on UNSAT input
+        std::vector<uint8_t> assignment(f.varnum), verified((std::size_t)R);
+        std::vector<int64_t> solved((std::size_t)R);
+        int64_t winner = -1, run = 0;
+        // states are generated on the device (main.rs:283-289 with a seeded generator)
+        system::check(odesat_simulate_batch(F.handle(), R, nullptr, nullptr, nullptr, seed, 0, &p, mode, 0, solved.data(),
+                                            verified.data(), &winner, assignment.data(), &run));
+        std::map<std::size_t, bool> values;                              // cnf.rs:301-315
+        for (const auto& kv : name_map) values[kv.first] = assignment[kv.second] != 0;
+        const bool ok = evaluate_cnf(values, raw);
+        std::printf("\nChecking if solution vector satisfies formula: %s\n", ok ? "true" : "false");
+        std::fprintf(stderr, "[odesat_b200] replicas=%lld steps_run=%lld winner=%lld\n", (long long)R, (long long)run, (long long)winner);
+        std::printf("Rendering variable assignments...\n");
+        std::string render;                                              // cnf.rs:289-298
+        for (const auto& kv : values) render += std::to_string(kv.first) + " " + (kv.second ? "1" : "0") + "\n";
+        if (!output.empty()) {
+            std::printf("Writing results to file...\n");
+            std::ofstream(output) << render;
+        } else {
+            std::printf("Variable assignments:\n%s\n", render.c_str());
+        }
+        return 0;
+    } catch (const system::Error& e) {
+        std::fprintf(stderr, "error: %s\n", e.what());
+        return 1;
+    }
+}

@@ -1,0 +1,46 @@
+"""End to end through the C++ host mirror: the `inter` / `batch` CLI with the reference's flags
+and console lines (main.rs:254-386) on the reference's fixtures."""
+import subprocess
+from pathlib import Path
+
+import pytest
+
+from odesat_b200 import cnf
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+CLI = ROOT / "odesat_b200" / "csrc" / "odesat_b200_cli"
+
+
+def run(*args):
+    return subprocess.run([str(CLI), *args], capture_output=True, text=True, timeout=300)
+
+
+def test_inter_on_the_satisfiable_fixture(tmp_path, golden_dir):
+    out = tmp_path / "assignment.txt"
+    r = run("inter", "-f", str(golden_dir / "aim100_sat.cnf"), "-b", "128", "-s", "0.01", "-n", "6000", "-o", str(out))
+    assert r.returncode == 0, r.stderr
+    for line in ("Reading CNF formula from file...", "Parsing CNF formula...", "Normalizing CNF formula...", "Simulating...",
+                 "Checking if solution vector satisfies formula: true", "Rendering variable assignments...",
+                 "Writing results to file..."):
+        assert line in r.stdout
+    # the written "<var> <0|1>" lines (cnf.rs:289-298) satisfy the original formula
+    values = {int(a): int(b) for a, b in (l.split() for l in out.read_text().splitlines())}
+    assert sorted(values) == list(range(1, 101))
+    f = cnf.parse_dimacs_format((golden_dir / "aim100_sat.cnf").read_text())
+    assert all(any((values[abs(l)] == 1) != (l < 0) for l in c) for c in f.clauses)
+
+
+def test_batch_on_the_unsat_fixture_is_configs1(golden_dir):
+    """BASELINE.json configs[1]: tests/hard.cnf `batch -b 100 -n 1000 -s 0.01` — UNSAT, never verifies."""
+    r = run("batch", "-f", str(golden_dir / "aim100_unsat.cnf"), "-b", "100", "-n", "1000", "-s", "0.01", "--f32")
+    assert r.returncode == 0, r.stderr
+    assert "Checking if solution vector satisfies formula: false" in r.stdout
+    assert "steps_run=1000" in r.stderr
+
+
+def test_solve_adaptive_and_usage_errors(golden_dir):
+    r = run("solve", "-f", str(golden_dir / "aim100_sat.cnf"), "-n", "20000", "--seed", "3")
+    assert r.returncode == 0 and "satisfies formula: true" in r.stdout
+    assert run("batch", "-f", str(golden_dir / "aim100_sat.cnf"), "-b", "4").returncode == 2      # -n is required (main.rs:96)
+    assert run("frobnicate").returncode == 2
