@@ -24,6 +24,7 @@ struct BatchBase {
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
     }
+    virtual void reset() = 0;   // flags, step counter, dt back to the state of a fresh batch
     virtual void init(uint64_t seed, int64_t replica_offset, bool gen_v, bool gen_xs, bool gen_xl) = 0;
     virtual void upload(const void* v, const void* xs, const void* xl, bool reset) = 0;
     virtual void download(void* v, void* xs, void* xl) = 0;
@@ -118,6 +119,8 @@ template <typename T> struct BatchImpl final : BatchBase {
         if (tile) tile->reset_control();
     }
 
+    void reset() override { reset_control(); }
+
     void ensure_staging() {
         const size_t need = (size_t)(std::max(f->N, f->M) * std::max<int64_t>(R, 1));
         if (staging.n < need) staging.alloc(need, &dev_bytes);
@@ -158,8 +161,20 @@ template <typename T> struct BatchImpl final : BatchBase {
         }
         return S[cur];
     }
-    void tile_to_canon() { if (tile) { launches += tile->export_state(S[0].v.p, S[0].xs.p, S[0].xl.p, Rp); } }
-    void canon_to_tile() { if (tile) { launches += tile->import_state(S[0].v.p, S[0].xs.p, S[0].xl.p, Rp); } }
+    bool canon_current = false;   // S[0] mirrors the tile engine's state (skip redundant exports)
+    void tile_to_canon() {
+        if (tile && !canon_current) {
+            canon();
+            launches += tile->export_state(S[0].v.p, S[0].xs.p, S[0].xl.p, Rp);
+            canon_current = true;
+        }
+    }
+    void canon_to_tile() {
+        if (tile) {
+            launches += tile->import_state(S[0].v.p, S[0].xs.p, S[0].xl.p, Rp);
+            canon_current = true;
+        }
+    }
 
     void init(uint64_t seed, int64_t replica_offset, bool gen_v, bool gen_xs, bool gen_xl) override {
         StateBuf<T>& s = canon();
@@ -236,6 +251,7 @@ template <typename T> struct BatchImpl final : BatchBase {
         ODESAT_REQUIRE(step + n < (int64_t(1) << 31) - 4, "step counter overflow");
         if (tile) {
             time_begin(ms);
+            if (n > 0) canon_current = false;
             launches += tile->run_fixed((T)dt, (T)zeta, n, freeze, solved.p, step);
             step += n;
             time_end(ms);

@@ -35,6 +35,11 @@ struct odesat_formula {
     // schedules keyed by kind * 4096 + warps per CTA
     mutable std::map<int, std::shared_ptr<odesat::TileLevels>> tile_levels;
     mutable std::map<int, std::shared_ptr<odesat::TileSchedule>> tile_sched;
+    // device buffers of the last odesat_simulate* call, reused by the next call of the same shape
+    // (allocating and freeing several GB per call costs more than the upload)
+    mutable std::shared_ptr<void> batch_cache;
+    mutable int64_t cache_R = -1;
+    mutable int cache_precision = -1, cache_engine = -1, cache_schedule = -1;
 
     double default_zeta() const {   // system.rs:164-173
         const double d = double(M) / double(N);

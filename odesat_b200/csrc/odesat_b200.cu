@@ -36,6 +36,23 @@ BatchBase* make_batch(const odesat_formula* f, int64_t R, int precision, int eng
     return new BatchImpl<double>(f, R, engine, schedule);
 }
 
+// Batch whose device buffers live on the formula handle and are reused by the next
+// odesat_simulate* call of the same shape.
+BatchBase* cached_batch(const odesat_formula* f, int64_t R, int precision, int engine, int schedule) {
+    ODESAT_REQUIRE(f != nullptr, "formula is NULL");
+    if (f->batch_cache && f->cache_R == R && f->cache_precision == precision && f->cache_engine == engine &&
+        f->cache_schedule == schedule) {
+        BatchBase* b = static_cast<BatchBase*>(f->batch_cache.get());
+        b->reset();
+        return b;
+    }
+    f->batch_cache.reset();   // free the old buffers before allocating the new ones
+    BatchBase* b = make_batch(f, R, precision, engine, schedule);
+    f->batch_cache = std::shared_ptr<void>(b, [](void* p) { delete static_cast<BatchBase*>(p); });
+    f->cache_R = R; f->cache_precision = precision; f->cache_engine = engine; f->cache_schedule = schedule;
+    return b;
+}
+
 // Host buffers of type TH feeding a device batch of precision `prec`.
 template <typename TH> struct HostIO {
     int prec;
@@ -160,7 +177,7 @@ void simulate_batch_impl(const odesat_formula* f, int64_t R, TH* v, TH* xs, TH* 
     if (mode == ODESAT_MODE_BATCH) ODESAT_REQUIRE(r.steps >= 0, "batch needs a step count (main.rs:96-97)");
     // the tile engine integrates fixed steps only: adaptive runs resolve AUTO to the gather engine
     const int eng = (!r.fixed && p->engine == ODESAT_ENGINE_AUTO) ? ODESAT_ENGINE_GATHER : p->engine;
-    std::unique_ptr<BatchBase> b(make_batch(f, R, p->precision, eng, p->schedule));
+    BatchBase* b = cached_batch(f, R, p->precision, eng, p->schedule);
     const int64_t NONE = std::numeric_limits<int64_t>::max();
     if (!(v && xs && xl)) b->init(seed, replica_offset, true, true, true);       // main.rs:283-289
     if (v || xs || xl) upload_host<TH>(*b, v, xs, xl, (v && xs && xl));
