@@ -58,7 +58,8 @@ template <typename T> struct BatchImpl final : BatchBase {
     StateBuf<T> S[2], H, Fb;
     int cur = 0;
     DevBuf<int32_t> solved;
-    DevBuf<uint32_t> unsat;     // ring [3][Rp]
+    DevBuf<uint32_t> unsat;     // [Rp]
+    DevBuf<T> contrib;          // [L][Rp] per-literal contributions (allocated on first use)
     DevBuf<U> err;
     DevBuf<T> dtv;
     DevBuf<T> staging;
@@ -90,9 +91,8 @@ template <typename T> struct BatchImpl final : BatchBase {
         if (engine == ODESAT_ENGINE_TILE) {
             tile.reset(new TileEngine<T>(*f, R, schedule, stream, &dev_bytes));
         } else {
-            S[0].alloc(N, M, Rp, &dev_bytes);
-            S[1].alloc(N, M, Rp, &dev_bytes);
-            unsat.alloc((size_t)std::max<int64_t>(3 * Rp, 1), &dev_bytes);
+            S[0].alloc(N, M, Rp, &dev_bytes);   // S[1] (derivatives / adaptive ping-pong) on first use
+            unsat.alloc((size_t)std::max<int64_t>(Rp, 1), &dev_bytes);
             err.alloc((size_t)std::max<int64_t>(Rp, 1), &dev_bytes);
         }
         reset_control();
@@ -120,6 +120,7 @@ template <typename T> struct BatchImpl final : BatchBase {
     }
 
     void reset() override { reset_control(); }
+    void ensure_alt() { if (!S[1].allocated()) S[1].alloc(f->N, f->M, Rp, &dev_bytes); }
 
     void ensure_staging() {
         const size_t need = (size_t)(std::max(f->N, f->M) * std::max<int64_t>(R, 1));
@@ -223,16 +224,39 @@ template <typename T> struct BatchImpl final : BatchBase {
         a.solved_step = solved.p;
         a.unsat = unsat.p;
         a.err = err.p;
+        if (contrib.n < (size_t)std::max<int64_t>(f->L * Rp, 1)) contrib.alloc((size_t)std::max<int64_t>(f->L * Rp, 1), &dev_bytes);
+        a.contrib = contrib.p;
         return a;
     }
 
-    template <int MODE> void launch_gather(const GatherArgs<T>& a) {
-        if (f->N + f->M == 0 || R == 0) return;
+    // one RHS evaluation + update = clause phase, then variable phase; 16 bytes of replicas per
+    // thread when the rows are 16-byte aligned (R >= 32 ⇒ Rp is a multiple of 32)
+    static constexpr int VW = 16 / (int)sizeof(T);
+    template <int V> void geom_v(int64_t rows, dim3& grid, dim3& block) const {
+        const int64_t rv = (R + V - 1) / V;
+        int bx = 1;
+        while (bx < 256 && bx < rv) bx <<= 1;
+        const int by = 256 / bx;
+        block = dim3(bx, by, 1);
+        const int64_t rpb = (int64_t)by * GATHER_ROWS_PER_BLOCK;
+        grid = dim3((unsigned)std::max<int64_t>((rows + rpb - 1) / rpb, 1), (unsigned)std::max<int64_t>((rv + bx - 1) / bx, 1), 1);
+    }
+    template <int MODE, int V> void launch_gather_v(const GatherArgs<T>& a) {
         dim3 g, b;
-        geom(f->N + f->M, g, b);
-        if (f->K == 3) k_gather<T, 3, MODE><<<g, b, 0, stream>>>(a);
-        else k_gather<T, 0, MODE><<<g, b, 0, stream>>>(a);
+        if (f->M > 0) {
+            geom_v<V>(f->M, g, b);
+            if (f->K == 3) k_clause_phase<T, 3, MODE, V><<<g, b, 0, stream>>>(a);
+            else k_clause_phase<T, 0, MODE, V><<<g, b, 0, stream>>>(a);
+            ++launches;
+        }
+        geom_v<V>(std::max<int64_t>(f->N, 1), g, b);
+        k_var_phase<T, MODE, V><<<g, b, 0, stream>>>(a);
         ++launches;
+    }
+    template <int MODE> void launch_gather(const GatherArgs<T>& a) {
+        if (R == 0) return;
+        if (Rp % VW == 0 && R >= 32) launch_gather_v<MODE, VW>(a);
+        else launch_gather_v<MODE, 1>(a);
     }
 
     void time_begin(float* ms) { if (ms) ODESAT_CUDA(cudaEventRecord(ev0, stream)); }
@@ -259,19 +283,14 @@ template <typename T> struct BatchImpl final : BatchBase {
         }
         time_begin(ms);
         for (int64_t i = 0; i < n; ++i) {
-            GatherArgs<T> a = base_args(zeta);
+            GatherArgs<T> a = base_args(zeta);   // in place: each element is read and written by its own thread
             a.v = S[cur].v.p; a.xs = S[cur].xs.p; a.xl = S[cur].xl.p;
-            a.ov = S[1 - cur].v.p; a.oxs = S[1 - cur].xs.p; a.oxl = S[1 - cur].xl.p;
+            a.ov = S[cur].v.p; a.oxs = S[cur].xs.p; a.oxl = S[cur].xl.p;
             a.dt = (T)dt;
             a.step = (int32_t)step;
             a.freeze = freeze;
             launch_gather<G_FIXED>(a);
-            cur = 1 - cur;
             ++step;
-        }
-        if (n > 0 && R > 0) {
-            k_fold_flags<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(solved.p, unsat.p, R, Rp, (int32_t)(step - 1));
-            ++launches;
         }
         time_end(ms);
     }
@@ -280,6 +299,7 @@ template <typename T> struct BatchImpl final : BatchBase {
         ODESAT_REQUIRE(n >= 0, "negative step count");
         ODESAT_REQUIRE(step + n < (int64_t(1) << 31) - 4, "step counter overflow");
         if (tile) throw Error(ODESAT_EUNSUPPORTED, "the tile engine integrates fixed steps only; use the gather engine for adaptive steps");
+        ensure_alt();
         if (!H.allocated()) { H.alloc(f->N, f->M, Rp, &dev_bytes); Fb.alloc(f->N, f->M, Rp, &dev_bytes); }
         time_begin(ms);
         for (int64_t i = 0; i < n; ++i) {
@@ -290,6 +310,7 @@ template <typename T> struct BatchImpl final : BatchBase {
             a.v = S[cur].v.p; a.xs = S[cur].xs.p; a.xl = S[cur].xl.p;
             a.ov = H.v.p; a.oxs = H.xs.p; a.oxl = H.xl.p;
             a.fv = Fb.v.p; a.fxs = Fb.xs.p; a.fxl = Fb.xl.p;
+            a.yv = S[cur].v.p; a.yxs = S[cur].xs.p; a.yxl = S[cur].xl.p;
             launch_gather<G_ADAPT_A>(a);
             // pass B: k2 on y_half → y_new, error norm
             a.yv = S[cur].v.p; a.yxs = S[cur].xs.p; a.yxl = S[cur].xl.p;
@@ -378,6 +399,7 @@ template <typename T> struct BatchImpl final : BatchBase {
     // ---- single-state helpers (gather engine only) ---------------------------------------
     void derivatives(double zeta, void* dv, void* dxs, void* dxl, int* allsat) override {
         ODESAT_REQUIRE(!tile, "derivatives() needs the gather engine");
+        ensure_alt();
         ODESAT_CUDA(cudaMemsetAsync(unsat.p, 0, unsat.bytes(), stream));
         GatherArgs<T> a = base_args(zeta);
         a.v = S[cur].v.p; a.xs = S[cur].xs.p; a.xl = S[cur].xl.p;
@@ -396,6 +418,7 @@ template <typename T> struct BatchImpl final : BatchBase {
 
     void update_state_with(const void* dv, const void* dxs, const void* dxl, double dt) override {
         ODESAT_REQUIRE(!tile, "update_state needs the gather engine");
+        ensure_alt();
         StateBuf<T>& d = S[1 - cur];
         put(dv, d.v.p, f->N);
         put(dxs, d.xs.p, f->M);
@@ -413,6 +436,7 @@ template <typename T> struct BatchImpl final : BatchBase {
 
     double max_error_vs(const void* bv, const void* bxs, const void* bxl) override {
         ODESAT_REQUIRE(!tile && R == 1, "max_error is a single-state call");
+        ensure_alt();
         StateBuf<T>& d = S[1 - cur];
         put(bv, d.v.p, f->N);
         put(bxs, d.xs.p, f->M);

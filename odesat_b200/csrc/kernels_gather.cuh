@@ -1,17 +1,21 @@
-// kernels_gather.cuh — the GENERAL engine: replica-major state, per-variable gather.
+// kernels_gather.cuh — the GENERAL engine: replica-major state, two phases per RHS evaluation.
 //
 // State layout in HBM: v[N][Rp], xs[M][Rp], xl[M][Rp] with the replica index fastest (Rp = R
-// padded to 32 elements), so the threads of a warp read one row for 32 consecutive replicas as
-// one coalesced 128/256-byte request.  With R = 1 the same kernels degenerate to one thread
-// per row (consecutive threads → consecutive rows), which is the single-instance path.
+// padded to 32 elements when R >= 32), so the threads of a warp read one row for consecutive
+// replicas as one coalesced request (16 bytes = 4 f32 / 2 f64 replicas per thread).  With R = 1
+// the same kernels degenerate to one thread per row (consecutive threads → consecutive rows),
+// which is the single-instance path.
 //
-// dv/dt is a deterministic GATHER, not a float-atomic scatter: the thread that owns (variable
-// i, replica r) walks i's occurrence list — sorted by (clause, literal position), i.e. the
-// order in which the reference's sequential loop reaches `dy.v[i] += …` (system.rs:35-80) —
-// re-evaluates each clause's min / second-min from the read-only input state and adds the
-// contributions starting from 0.0.  Sums are therefore bit-identical to the reference's.
-// State is double-buffered (read t, write t+1) so one launch is one Euler step with no
-// grid-wide barrier.
+// dv/dt is a deterministic scatter-then-gather, not a float-atomic scatter:
+//   clause phase   thread (clause m, replicas r..) evaluates the clause once — min / second-min,
+//                  C_m, the memory derivatives, the satisfied flag — and writes the contribution
+//                  of each of its literals to contrib[slot][r] (slot = position in the CSR);
+//   variable phase thread (variable i, replicas r..) adds contrib[slot][r] over i's occurrence
+//                  list, which is sorted by (clause, literal position) — the order in which the
+//                  reference's sequential loop reaches `dy.v[i] += …` (system.rs:35-80) —
+//                  starting from 0.0.  Sums are therefore bit-identical to the reference's.
+// Every clause is evaluated exactly once per RHS (a single-pass gather would re-evaluate it once
+// per literal: 15 state words per clause instead of 5).  FIXED steps update the state in place.
 #pragma once
 #include "common.cuh"
 
@@ -23,153 +27,283 @@ template <typename T> struct GatherArgs {
     FormulaDev f;
     int64_t R = 0, Rp = 0;
     const T *v = nullptr, *xs = nullptr, *xl = nullptr;   // state the RHS is evaluated on
-    T *ov = nullptr, *oxs = nullptr, *oxl = nullptr;      // FIXED: y(t+1); DERIV: dy; A: y_half; B: y_new
+    T *ov = nullptr, *oxs = nullptr, *oxl = nullptr;      // FIXED: y(t+1) (may alias the inputs); DERIV: dy; A: y_half; B: y_new
     T *fv = nullptr, *fxs = nullptr, *fxl = nullptr;      // A: y_full (out); B: y_full (in)
     const T *yv = nullptr, *yxs = nullptr, *yxl = nullptr;   // B: the step's original y (copied through when done)
+    T* contrib = nullptr;         // [L][Rp] per-literal contributions to dv
     T dt = T(0);
     const T* dt_arr = nullptr;    // per-replica dt (adaptive); overrides dt
     T zeta = T(0);
     T xl_max = T(0);              // 1e4 * M (system.rs:95)
     int32_t* solved_step = nullptr;   // [R] first flagged step, -1 = none
-    uint32_t* unsat = nullptr;    // FIXED: ring [3][Rp]; others: [Rp]
+    uint32_t* unsat = nullptr;    // [Rp] "some clause of this replica is unsatisfied" for the current RHS
     typename ErrBits<T>::U* err = nullptr;   // [Rp] (B)
     int32_t step = 0;
     int32_t freeze = 0;
 };
 
-// system.rs:43-57: running min / second-min over the literals of clause m for one replica.
-template <typename T, int K>
-__device__ __forceinline__ void clause_min2(const FormulaDev& f, const T* __restrict__ v, int64_t Rp,
-                                            int64_t rep, int m, T& mn, T& sm) {
-    mn = inf_v<T>();
-    sm = inf_v<T>();
-    int b, e;
-    if (K > 0) { b = m * K; e = b + K; }
-    else { b = __ldg(f.coff + m); e = __ldg(f.coff + m + 1); }
+template <typename T> __device__ __forceinline__ void err_max(typename ErrBits<T>::U* slot, T e) {
+    if (e == e) {   // NaN-ignoring, like the reference's folds (system.rs:103)
+        const typename ErrBits<T>::U b = ErrBits<T>::enc(e);
+        if (b > *slot) atomicMax(slot, b);
+    }
+}
+
+// V consecutive replicas per thread (16-byte accesses when V·sizeof(T) == 16, scalar when V == 1).
+template <typename T, int V> struct RVec { T x[V]; };
+template <typename T, int V> __device__ __forceinline__ RVec<T, V> vload(const T* p) {   // read-only in this launch
+    RVec<T, V> r;
+    if (V * sizeof(T) == 16) {
+        const int4 q = __ldg(reinterpret_cast<const int4*>(p));
+        *reinterpret_cast<int4*>(r.x) = q;
+    } else {
 #pragma unroll
-    for (int j = b; j < e; ++j) {
-        const int lit = __ldg(f.lits + j);
+        for (int u = 0; u < V; ++u) r.x[u] = __ldg(p + u);
+    }
+    return r;
+}
+template <typename T, int V> __device__ __forceinline__ RVec<T, V> vload_rw(const T* p) {   // data this launch may also write
+    RVec<T, V> r;
+    if (V * sizeof(T) == 16) *reinterpret_cast<int4*>(r.x) = *reinterpret_cast<const int4*>(p);
+    else {
+#pragma unroll
+        for (int u = 0; u < V; ++u) r.x[u] = p[u];
+    }
+    return r;
+}
+template <typename T, int V> __device__ __forceinline__ void vstore(T* p, const RVec<T, V>& r) {
+    if (V * sizeof(T) == 16) *reinterpret_cast<int4*>(p) = *reinterpret_cast<const int4*>(r.x);
+    else {
+#pragma unroll
+        for (int u = 0; u < V; ++u) p[u] = r.x[u];
+    }
+}
+
+constexpr int GATHER_ROWS_PER_BLOCK = 8;   // rows a thread walks per launch: fewer, fatter blocks
+
+// ---- clause phase: system.rs:41-88 for one clause and V replicas ----------------------------
+template <typename T, int K, int MODE, int V>
+__device__ __forceinline__ void clause_row(const GatherArgs<T>& a, int64_t m, int64_t rep) {
+    const int64_t Rp = a.Rp;
+    const int64_t at = m * Rp + rep;
+    bool skip[V];   // element is frozen / done / beyond R: keep (or pass through) its state
+    bool all_skip = true;
+#pragma unroll
+    for (int u = 0; u < V; ++u) {
+        const bool in = rep + u < a.R;
+        bool sk = !in;
+        if (in) {
+            if (MODE == G_FIXED) sk = a.freeze && a.solved_step[rep + u] >= 0;
+            else if (MODE == G_ADAPT_A) sk = a.solved_step[rep + u] >= 0;
+            else if (MODE == G_ADAPT_B) sk = a.solved_step[rep + u] >= 0 || a.unsat[rep + u] == 0u;
+        }
+        skip[u] = sk;
+        all_skip = all_skip && sk;
+    }
+    if (all_skip) {
+        if (MODE == G_ADAPT_B) {   // done / just flagged: state untouched (system.rs:122)
+            vstore<T, V>(a.oxs + at, vload<T, V>(a.yxs + at));
+            vstore<T, V>(a.oxl + at, vload<T, V>(a.yxl + at));
+        }
+        return;
+    }
+    T dt[V];
+#pragma unroll
+    for (int u = 0; u < V; ++u) dt[u] = a.dt_arr ? a.dt_arr[rep + u < a.R ? rep + u : rep] : a.dt;
+    int b, e;
+    if (K > 0) { b = (int)m * K; e = b + K; }
+    else { b = __ldg(a.f.coff + m); e = __ldg(a.f.coff + m + 1); }
+    T mn[V], sm[V];
+#pragma unroll
+    for (int u = 0; u < V; ++u) { mn[u] = inf_v<T>(); sm[u] = inf_v<T>(); }
+    RVec<T, V> vis[K > 0 ? K : 1];
+    T qs[K > 0 ? K : 1];
+#pragma unroll
+    for (int j = b; j < e; ++j) {                              // :46-57
+        const int lit = __ldg(a.f.lits + j);
         const int var = (lit < 0 ? -lit : lit) - 1;
         const T q = lit < 0 ? T(-1) : T(1);
-        const T vi = __ldg(v + (int64_t)var * Rp + rep);
-        const T val = T(1) - q * vi;                       // :49
-        if (val < mn) { sm = mn; mn = val; }               // :50-52
-        else if (val < sm) { sm = val; }                   // :53-55
+        const RVec<T, V> vi = vload_rw<T, V>(a.v + (int64_t)var * Rp + rep);
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+            const T val = T(1) - q * vi.x[u];                  // :49
+            if (val < mn[u]) { sm[u] = mn[u]; mn[u] = val; }   // :50-52
+            else if (val < sm[u]) { sm[u] = val; }             // :53-55
+        }
+        if (K > 0) { vis[j - b] = vi; qs[j - b] = q; }
     }
-}
-
-template <typename T, int K, int MODE>
-__global__ void __launch_bounds__(256) k_gather(const GatherArgs<T> a) {
-    const int64_t rep = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
-    const int64_t row = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
-    const int64_t N = a.f.N, M = a.f.M, Rp = a.Rp;
-    if (rep >= a.R || row >= N + M) return;
-
-    bool passthru = false;   // replica is frozen/done: copy instead of integrate
-    if (MODE == G_FIXED) {
-        const int ss = a.solved_step[rep];
-        const bool prev = (a.step > 0) && (a.unsat[(int64_t)((a.step + 2) % 3) * Rp + rep] == 0u);
-        if (row == 0) {
-            if (ss < 0 && prev) a.solved_step[rep] = a.step - 1;
-            a.unsat[(int64_t)((a.step + 1) % 3) * Rp + rep] = 0u;
-        }
-        passthru = a.freeze && (ss >= 0 || prev);
-    } else if (MODE == G_ADAPT_A) {
-        if (a.solved_step[rep] >= 0) return;
-    } else if (MODE == G_ADAPT_B) {
-        passthru = (a.solved_step[rep] >= 0) || (a.unsat[rep] == 0u);
+    const RVec<T, V> xs_m = vload_rw<T, V>(a.xs + at), xl_m = vload_rw<T, V>(a.xl + at);
+    T c[V], w[V], rg[V];
+#pragma unroll
+    for (int u = 0; u < V; ++u) {
+        c[u] = T(0.5) * mn[u];                                 // :60
+        w[u] = xl_m.x[u] * xs_m.x[u];
+        rg[u] = (T(1) + a.zeta * xl_m.x[u]) * (T(1) - xs_m.x[u]);
     }
-    const T dt = a.dt_arr ? a.dt_arr[rep] : a.dt;
-
-    if (row < N) {
-        // ---------------- variable row: dv by ordered gather, then the v update ----------
-        const int64_t at = row * Rp + rep;
-        if (passthru) { a.ov[at] = (MODE == G_ADAPT_B) ? a.yv[at] : a.v[at]; return; }
-        const T vi = __ldg(a.v + at);
-        T dv = T(0);                                                     // :33
-        const int e0 = __ldg(a.f.voff + row), e1 = __ldg(a.f.voff + row + 1);
-        for (int e = e0; e < e1; ++e) {
-            const int m = __ldg(a.f.occ_clause + e);
-            T mn, sm;
-            clause_min2<T, K>(a.f, a.v, Rp, rep, m, mn, sm);
-            const T c = T(0.5) * mn;                                     // :60
-            const int lit = __ldg(a.f.lits + __ldg(a.f.occ_slot + e));
-            const T q = lit < 0 ? T(-1) : T(1);
-            const T val = T(1) - q * vi;
-            const T g = (T(0.5) * q) * ((val != mn) ? mn : sm);          // :64-70
-            const T r = (c == val) ? T(0.5) * (q - vi) : T(0);           // :73-77
-            const T xs_m = __ldg(a.xs + (int64_t)m * Rp + rep);
-            const T xl_m = __ldg(a.xl + (int64_t)m * Rp + rep);
-            dv = dv + ((xl_m * xs_m) * g + ((T(1) + a.zeta * xl_m) * (T(1) - xs_m)) * r);   // :80
+#pragma unroll
+    for (int j = b; j < e; ++j) {                              // :62-81
+        RVec<T, V> vi;
+        T q;
+        if (K > 0) { vi = vis[j - b]; q = qs[j - b]; }
+        else {
+            const int lit = __ldg(a.f.lits + j);
+            const int var = (lit < 0 ? -lit : lit) - 1;
+            q = lit < 0 ? T(-1) : T(1);
+            vi = vload_rw<T, V>(a.v + (int64_t)var * Rp + rep);
         }
-        if (MODE == G_DERIV) { a.ov[at] = dv; }
-        else if (MODE == G_FIXED) { a.ov[at] = euler_clamp(vi, dv, dt, T(-1), T(1)); }   // :96
-        else if (MODE == G_ADAPT_A) {
-            a.ov[at] = euler_clamp(vi, dv, T(0.5) * dt, T(-1), T(1));    // :128
-            a.fv[at] = euler_clamp(vi, dv, dt, T(-1), T(1));             // :125
-        } else {
-            const T yn = euler_clamp(vi, dv, T(0.5) * dt, T(-1), T(1));  // :130
-            a.ov[at] = yn;
-            const T e = fabs(a.fv[at] - yn);                             // :102-103
-            if (e == e) {
-                const typename ErrBits<T>::U b = ErrBits<T>::enc(e);
-                if (b > a.err[rep]) atomicMax(a.err + rep, b);
-            }
+        RVec<T, V> t;
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+            const T val = T(1) - q * vi.x[u];
+            const T g = (T(0.5) * q) * ((val != mn[u]) ? mn[u] : sm[u]);         // :64-70
+            const T r = (c[u] == val) ? T(0.5) * (q - vi.x[u]) : T(0);           // :73-77
+            t.x[u] = w[u] * g + rg[u] * r;                                       // the addend of :80
         }
-    } else {
-        // ---------------- clause row: C_m, the memories, the satisfied flag ----------------
-        const int m = (int)(row - N);
-        const int64_t at = (int64_t)m * Rp + rep;
-        if (passthru) {
-            a.oxs[at] = (MODE == G_ADAPT_B) ? a.yxs[at] : a.xs[at];
-            a.oxl[at] = (MODE == G_ADAPT_B) ? a.yxl[at] : a.xl[at];
-            return;
-        }
-        T mn, sm;
-        clause_min2<T, K>(a.f, a.v, Rp, rep, m, mn, sm);
-        const T c = T(0.5) * mn;
-        const T xs_m = __ldg(a.xs + at), xl_m = __ldg(a.xl + at);
-        const T dxs = (Kc<T>::BETA * (xs_m + Kc<T>::EPSILON)) * (c - Kc<T>::GAMMA);   // :84
-        const T dxl = Kc<T>::ALPHA * (c - Kc<T>::DELTA);                               // :85
-        const bool sat = c < Kc<T>::GAMMA;                                             // :88
-        const T hi_s = T(1) - Kc<T>::EPSILON;
+        vstore<T, V>(a.contrib + (int64_t)j * Rp + rep, t);
+    }
+    const T hi_s = T(1) - Kc<T>::EPSILON;
+    RVec<T, V> o1, o2, f1, f2;
+#pragma unroll
+    for (int u = 0; u < V; ++u) {
+        const T x = xs_m.x[u], l = xl_m.x[u];
+        const T dxs = (Kc<T>::BETA * (x + Kc<T>::EPSILON)) * (c[u] - Kc<T>::GAMMA);   // :84
+        const T dxl = Kc<T>::ALPHA * (c[u] - Kc<T>::DELTA);                            // :85
+        if (MODE != G_ADAPT_B && !skip[u] && !(c[u] < Kc<T>::GAMMA)) a.unsat[rep + u] = 1u;   // :88 (B's flag is discarded, :129)
         if (MODE == G_FIXED) {
-            if (!sat) a.unsat[(int64_t)(a.step % 3) * Rp + rep] = 1u;
-            a.oxs[at] = euler_clamp(xs_m, dxs, dt, Kc<T>::EPSILON, hi_s);              // :94
-            a.oxl[at] = euler_clamp(xl_m, dxl, dt, T(1), a.xl_max);                    // :95
+            o1.x[u] = skip[u] ? x : euler_clamp(x, dxs, dt[u], Kc<T>::EPSILON, hi_s);  // :94
+            o2.x[u] = skip[u] ? l : euler_clamp(l, dxl, dt[u], T(1), a.xl_max);        // :95
         } else if (MODE == G_DERIV) {
-            if (!sat) a.unsat[rep] = 1u;
-            a.oxs[at] = dxs;
-            a.oxl[at] = dxl;
+            o1.x[u] = dxs;
+            o2.x[u] = dxl;
         } else if (MODE == G_ADAPT_A) {
-            if (!sat) a.unsat[rep] = 1u;
-            const T h = T(0.5) * dt;
-            a.oxs[at] = euler_clamp(xs_m, dxs, h, Kc<T>::EPSILON, hi_s);
-            a.oxl[at] = euler_clamp(xl_m, dxl, h, T(1), a.xl_max);
-            a.fxs[at] = euler_clamp(xs_m, dxs, dt, Kc<T>::EPSILON, hi_s);
-            a.fxl[at] = euler_clamp(xl_m, dxl, dt, T(1), a.xl_max);
+            const T h = T(0.5) * dt[u];
+            o1.x[u] = euler_clamp(x, dxs, h, Kc<T>::EPSILON, hi_s);                    // :128
+            o2.x[u] = euler_clamp(l, dxl, h, T(1), a.xl_max);
+            f1.x[u] = euler_clamp(x, dxs, dt[u], Kc<T>::EPSILON, hi_s);                // :125
+            f2.x[u] = euler_clamp(l, dxl, dt[u], T(1), a.xl_max);
         } else {
-            const T h = T(0.5) * dt;
-            const T ns = euler_clamp(xs_m, dxs, h, Kc<T>::EPSILON, hi_s);
-            const T nl = euler_clamp(xl_m, dxl, h, T(1), a.xl_max);
-            a.oxs[at] = ns;
-            a.oxl[at] = nl;
-            const T e1 = fabs(a.fxs[at] - ns), e2 = fabs(a.fxl[at] - nl);
-            T e = rmax(e1, e2);   // NaN-ignoring, like the reference's folds
-            if (e == e) {
-                const typename ErrBits<T>::U b = ErrBits<T>::enc(e);
-                if (b > a.err[rep]) atomicMax(a.err + rep, b);
-            }
+            const T h = T(0.5) * dt[u];
+            o1.x[u] = euler_clamp(x, dxs, h, Kc<T>::EPSILON, hi_s);                    // :130
+            o2.x[u] = euler_clamp(l, dxl, h, T(1), a.xl_max);
         }
+    }
+    if (MODE == G_ADAPT_A) {
+        // skipped elements of a mixed vector: their H/F rows are never read (pass B copies y through)
+        vstore<T, V>(a.fxs + at, f1);
+        vstore<T, V>(a.fxl + at, f2);
+    }
+    if (MODE == G_ADAPT_B) {
+        const RVec<T, V> yx = vload<T, V>(a.yxs + at), yl = vload<T, V>(a.yxl + at);
+        const RVec<T, V> fx = vload<T, V>(a.fxs + at), fl = vload<T, V>(a.fxl + at);
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+            if (skip[u]) { o1.x[u] = yx.x[u]; o2.x[u] = yl.x[u]; }
+            else if (rep + u < a.R) err_max<T>(a.err + rep + u, rmax(fabs(fx.x[u] - o1.x[u]), fabs(fl.x[u] - o2.x[u])));   // :104-107
+        }
+    }
+    vstore<T, V>(a.oxs + at, o1);
+    vstore<T, V>(a.oxl + at, o2);
+}
+
+template <typename T, int K, int MODE, int V>
+__global__ void __launch_bounds__(256) k_clause_phase(const GatherArgs<T> a) {
+    const int64_t rep = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * V;
+    if (rep >= a.R) return;
+#pragma unroll 2
+    for (int it = 0; it < GATHER_ROWS_PER_BLOCK; ++it) {
+        const int64_t m = ((int64_t)blockIdx.x * GATHER_ROWS_PER_BLOCK + it) * blockDim.y + threadIdx.y;
+        if (m < a.f.M) clause_row<T, K, MODE, V>(a, m, rep);
     }
 }
 
-// After the last FIXED step of a run: fold that step's flags into solved_step.
-__global__ void k_fold_flags(int32_t* solved_step, const uint32_t* unsat_ring, int64_t R, int64_t Rp,
-                             int32_t last_step) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R || last_step < 0) return;
-    if (solved_step[r] < 0 && unsat_ring[(int64_t)(last_step % 3) * Rp + r] == 0u) solved_step[r] = last_step;
+// ---- variable phase: the ordered sum of :80 and the v update of :96 ----------------------------
+// Row 0 of every replica also commits the replica's flag (FIXED): the clause phase of step s has
+// finished when this kernel runs, so unsat[r] is the complete AND of :90.
+template <typename T, int MODE, int V>
+__device__ __forceinline__ void var_row(const GatherArgs<T>& a, int64_t row, int64_t rep) {
+    const int64_t N = a.f.N, Rp = a.Rp;
+    bool skip[V];
+    bool all_skip = true;
+#pragma unroll
+    for (int u = 0; u < V; ++u) {
+        const bool in = rep + u < a.R;
+        bool sk = !in;
+        if (in) {
+            if (MODE == G_FIXED) {
+                const int ss = a.solved_step[rep + u];
+                sk = a.freeze && ss >= 0 && ss < a.step;      // flagged in an EARLIER step
+                if (row == 0) {
+                    if (ss < 0 && a.unsat[rep + u] == 0u) a.solved_step[rep + u] = a.step;   // the update below still happens (:149-153)
+                    a.unsat[rep + u] = 0u;
+                }
+            } else if (MODE == G_ADAPT_A) sk = a.solved_step[rep + u] >= 0;
+            else if (MODE == G_ADAPT_B) sk = a.solved_step[rep + u] >= 0 || a.unsat[rep + u] == 0u;
+        }
+        skip[u] = sk;
+        all_skip = all_skip && sk;
+    }
+    if (row >= N) return;
+    const int64_t at = row * Rp + rep;
+    if (all_skip) {
+        if (MODE == G_ADAPT_B) vstore<T, V>(a.ov + at, vload<T, V>(a.yv + at));
+        return;
+    }
+    const RVec<T, V> vi = vload_rw<T, V>(a.v + at);
+    T dv[V];
+#pragma unroll
+    for (int u = 0; u < V; ++u) dv[u] = T(0);                         // :33
+    const int e0 = __ldg(a.f.voff + row), e1 = __ldg(a.f.voff + row + 1);
+    for (int e = e0; e < e1; e += 4) {                                // 4 independent row loads in flight, added in order
+        RVec<T, V> t[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (e + k < e1) t[k] = vload_rw<T, V>(a.contrib + (int64_t)__ldg(a.f.occ_slot + e + k) * Rp + rep);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (e + k < e1) {
+#pragma unroll
+                for (int u = 0; u < V; ++u) dv[u] = dv[u] + t[k].x[u];   // :80
+            }
+    }
+    RVec<T, V> o, fo;
+    if (MODE == G_ADAPT_B) {
+        const RVec<T, V> y = vload<T, V>(a.yv + at), fv = vload<T, V>(a.fv + at);
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+            const T dt = a.dt_arr ? a.dt_arr[rep + u < a.R ? rep + u : rep] : a.dt;
+            const T yn = euler_clamp(vi.x[u], dv[u], T(0.5) * dt, T(-1), T(1));      // :130
+            if (skip[u]) o.x[u] = y.x[u];
+            else {
+                o.x[u] = yn;
+                if (rep + u < a.R) err_max<T>(a.err + rep + u, fabs(fv.x[u] - yn));   // :102-103
+            }
+        }
+        vstore<T, V>(a.ov + at, o);
+        return;
+    }
+#pragma unroll
+    for (int u = 0; u < V; ++u) {
+        const T dt = a.dt_arr ? a.dt_arr[rep + u < a.R ? rep + u : rep] : a.dt;
+        if (MODE == G_DERIV) o.x[u] = dv[u];
+        else if (MODE == G_FIXED) o.x[u] = skip[u] ? vi.x[u] : euler_clamp(vi.x[u], dv[u], dt, T(-1), T(1));   // :96
+        else {
+            o.x[u] = euler_clamp(vi.x[u], dv[u], T(0.5) * dt, T(-1), T(1));          // :128
+            fo.x[u] = euler_clamp(vi.x[u], dv[u], dt, T(-1), T(1));                  // :125
+        }
+    }
+    vstore<T, V>(a.ov + at, o);
+    if (MODE == G_ADAPT_A) vstore<T, V>(a.fv + at, fo);
+}
+
+template <typename T, int MODE, int V>
+__global__ void __launch_bounds__(256) k_var_phase(const GatherArgs<T> a) {
+    const int64_t rep = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * V;
+    if (rep >= a.R) return;
+    const int64_t rows = a.f.N > 0 ? a.f.N : 1;
+    for (int it = 0; it < GATHER_ROWS_PER_BLOCK; ++it) {
+        const int64_t row = ((int64_t)blockIdx.x * GATHER_ROWS_PER_BLOCK + it) * blockDim.y + threadIdx.y;
+        if (row < rows) var_row<T, MODE, V>(a, row, rep);
+    }
 }
 
 // Adaptive pass C (system.rs:132-135): per replica, commit the flag or update dt.

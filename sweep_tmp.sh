@@ -1,6 +1,4 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -2 gpurun_out/pytest_gpu.log
-python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/bench_default.json').read().strip().splitlines()[-1])
-print({k:d[k] for k in ('value','ms_per_step','e2e','gpu_launches')})
-PY
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; grep -E "passed|failed|Error" gpurun_out/pytest_gpu.log | tail -3
+python bench.py --quick --steps 20 --warmup 3 --engine gather 2>&1 | tail -1 | cut -c1-200
+python bench.py --quick --steps 10 --warmup 3 --workload rand50k --replicas 2048 2>&1 | tail -1 | cut -c1-200
+python bench.py --quick --steps 20 --warmup 3 --engine gather --precision f64 --replicas 2048 2>&1 | tail -1 | cut -c1-200
