@@ -40,6 +40,10 @@ def workload(args):
     elif args.workload == "rand50k":
         f = cnf.random_ksat(50_000, 4.25, seed=20240611 + 4)
         name = f"random 3-SAT N=50000 alpha=4.25, {args.replicas} replicas/GPU, fixed step dt=0.01"
+    elif args.workload == "rand1m":
+        f = cnf.random_ksat(1_000_000, 4.2, seed=20240611 + 3)
+        args.replicas = 1
+        name = "random 3-SAT N=1000000 alpha=4.2 M=4200000, single instance, adaptive step tol=1e-3 (2 RHS evaluations per step)"
     elif args.workload == "hard":
         f = cnf.load_dimacs(str(ROOT / "tests" / "golden" / "aim100_unsat.cnf"))
         name = f"tests/hard.cnf (aim-100 UNSAT), {args.replicas} replicas/GPU, fixed step dt=0.01"
@@ -48,8 +52,11 @@ def workload(args):
     return f, name
 
 
-def algorithmic_bytes_per_step(N, M, Lits, R, P):
-    """every state element read once and written once, formula CSR read once."""
+def algorithmic_bytes_per_step(N, M, Lits, R, P, adaptive=False):
+    """every state element read once and written once, formula CSR read once
+    (adaptive: pass A reads y, writes y_half and y_full; pass B reads both, writes y_new)."""
+    if adaptive:
+        return R * 6 * P * (N + 2 * M) + 2 * (4 * Lits + 4 * (M + 1))
     return R * 2 * P * (N + 2 * M) + 4 * Lits + 4 * (M + 1)
 
 
@@ -211,12 +218,19 @@ def run_gpu(args):
     b.init(RUN_SEED, rank * R)
     eng_name = {L.ENGINE_GATHER: "gather", L.ENGINE_TILE: "tile"}[b.engine]
 
+    adaptive = args.workload == "rand1m"
+
+    def run(n, timed=False):
+        if adaptive:
+            return b.run_adaptive(1e-3, zeta, n, timed=timed)
+        return b.run_fixed(DT, zeta, n, freeze=False, timed=timed)
+
     # ---- device-resident throughput: W warm-up steps, then exactly K timed steps --------------
-    b.run_fixed(DT, zeta, args.warmup, freeze=False)
+    run(args.warmup)
     launches0 = b.launches
     barrier()
     with ClockSampler(local) as clk:
-        ms = b.run_fixed(DT, zeta, args.steps, freeze=False, timed=True)
+        ms = run(args.steps, timed=True)
     barrier()
     n_launch = b.launches - launches0
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -225,13 +239,23 @@ def run_gpu(args):
     ms_max = float(t.item())
     evals = args.steps * f.n_clauses * R * world
     value = evals / (ms_max * 1e-3)
-    bytes_step = algorithmic_bytes_per_step(f.varnum, f.n_clauses, f.n_literals, R, P)
+    bytes_step = algorithmic_bytes_per_step(f.varnum, f.n_clauses, f.n_literals, R, P, adaptive)
     achieved = bytes_step * args.steps / (ms * 1e-3) / 1e9
     peak, peak_src = measured_peak()
     st, _ = b.status()
     flagged = int((st >= 0).sum())
     b.close()
     other = None
+    if args.quick or adaptive:
+        if rank == 0:
+            print(json.dumps({"quick": True, "workload": args.workload, "engine": eng_name, "schedule": args.schedule,
+                              "precision": args.precision, "ms_per_step": ms_max / args.steps, "value": value,
+                              "frac": achieved / peak, "frac_of_8TBs": achieved / 8000.0, "launches": n_launch,
+                              "flagged": flagged, "env": {k: v for k, v in os.environ.items() if k.startswith("ODESAT_")}}))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     if not args.quick and eng_name == "tile":
         # the same K steps with the other clause schedule, for the record (not the headline value)
         osched = L.SCHED_EXACT if sched == L.SCHED_BALANCED else L.SCHED_BALANCED
@@ -242,16 +266,6 @@ def run_gpu(args):
         ob.close()
         other = {"schedule": "exact" if osched == L.SCHED_EXACT else "balanced", "ms_per_step": oms / args.steps,
                  "roofline_frac": bytes_step * args.steps / (oms * 1e-3) / 1e9 / peak}
-
-    if args.quick:
-        if rank == 0:
-            print(json.dumps({"quick": True, "engine": eng_name, "schedule": args.schedule, "ms_per_step": ms_max / args.steps,
-                              "value": value, "frac": achieved / peak, "frac_of_8TBs": achieved / 8000.0,
-                              "launches": n_launch, "env": {k: v for k, v in os.environ.items() if k.startswith("ODESAT_")}}))
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
 
     # ---- end to end through the C ABI with HOST (pinned) buffers ------------------------------
     dt_t = torch.float32 if prec == L.F32 else torch.float64
@@ -327,7 +341,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="rand10k", choices=["rand10k", "rand50k", "hard"])
+    ap.add_argument("--workload", default="rand10k", choices=["rand10k", "rand50k", "rand1m", "hard"])
     ap.add_argument("--replicas", type=int, default=4096, help="replicas per GPU")
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--engine", default="auto", choices=["auto", "gather", "tile"])

@@ -265,3 +265,21 @@ def test_error_paths(golden_dir):
     DE = S.DeviceFormula(e)
     y = S.State(np.array([0.1, -0.2, 0.3, 0.0]), np.zeros(0), np.zeros(0))
     assert S.euler_step_fixed(y, DE, 0.01, 0.001) is True
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_large_single_instance_adaptive_and_fixed(dtype):
+    """Single large instance (the shape of BASELINE configs[3], scaled to what the oracle does in
+    seconds): N = 200 000, alpha = 4.2, R = 1 — adaptive and fixed steps bit-exact."""
+    f = cnf.random_ksat(200_000, 4.2, seed=20240614)
+    D, F = both(f)
+    v = F.init_v0(1, 0, dtype); xs = F.init_short_term_memory(dtype); xl = np.ones(F.M, dtype)
+    st = S.State(v.copy(), xs.copy(), xl.copy())
+    info = []
+    S.simulate(st, D, 1e-3, None, 6, None, info=info)
+    oa, oflag, osteps, odt = F.simulate(v, xs, xl, tol=1e-3, steps=6)
+    assert info[0].steps_taken == osteps == 6 and info[0].final_dt == odt
+    assert eq(st.v, v) and eq(st.xs, xs) and eq(st.xl, xl)
+    S.simulate(st, D, None, 0.01, 5, None)
+    F.simulate(v, xs, xl, step_size=0.01, steps=5)
+    assert eq(st.v, v) and eq(st.xs, xs) and eq(st.xl, xl)
