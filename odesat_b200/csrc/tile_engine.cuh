@@ -141,6 +141,73 @@ __device__ __forceinline__ void clause_math(const T (&v)[3], T (&d)[3], const T 
     }
 }
 
+// ---- packed f32x2 arithmetic (sm_100a FADD2 / FMUL2 / FFMA2) --------------------------------
+// The two f32 replicas of a tile sit in adjacent registers (rows are {v0, v1, dv0, dv1}), so every
+// add / mul / fma of the clause arithmetic is issued once for both.  Each lane is an IEEE
+// round-to-nearest operation without flush-to-zero, i.e. bit-identical to the scalar instruction.
+__device__ __forceinline__ unsigned long long pk2(float2 a) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
+}
+__device__ __forceinline__ float2 up2(unsigned long long v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)));
+    return up2(r);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)));
+    return up2(r);
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)), "l"(pk2(c)));
+    return up2(r);
+}
+__device__ __forceinline__ float2 bc2(float x) { return make_float2(x, x); }
+
+// Fast path of clause_math for the two f32 replicas of a tile at once (same operations in the same
+// order as clause_math<float, false>, the add / mul / fma ones packed).
+__device__ __forceinline__ void clause_math_f32x2(const float2 (&v)[3], float2 (&d)[3], const float (&q)[3], float2& xs, float2& xl,
+                                                  bool (&unsat)[2], float2 dt, float xl_max) {
+    const float hi_s = 1.0f - Kc<float>::EPSILON;
+    float2 a[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) a[j] = fma2(bc2(-q[j]), v[j], bc2(1.0f));
+    float2 mn, sm;
+    {
+        const float lo = rmin(a[0].x, a[1].x), hi = rmax(a[0].x, a[1].x);
+        mn.x = rmin(lo, a[2].x);
+        sm.x = rmax(lo, rmin(hi, a[2].x));
+    }
+    {
+        const float lo = rmin(a[0].y, a[1].y), hi = rmax(a[0].y, a[1].y);
+        mn.y = rmin(lo, a[2].y);
+        sm.y = rmax(lo, rmin(hi, a[2].y));
+    }
+    const float2 cm = mul2(bc2(0.5f), mn);                                  // :60
+    const float2 h = mul2(bc2(0.5f), mul2(xl, xs));
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float2 sel = make_float2((a[j].x != mn.x) ? mn.x : sm.x, (a[j].y != mn.y) ? mn.y : sm.y);
+        d[j] = fma2(mul2(h, sel), bc2(q[j]), d[j]);                         // :64-70, :80
+    }
+    const float2 dxs = mul2(mul2(bc2(Kc<float>::BETA), add2(xs, bc2(Kc<float>::EPSILON))), add2(cm, bc2(-Kc<float>::GAMMA)));   // :84
+    const float2 dxl = mul2(bc2(Kc<float>::ALPHA), add2(cm, bc2(-Kc<float>::DELTA)));                                           // :85
+    unsat[0] = unsat[0] || !(cm.x < Kc<float>::GAMMA);                      // :88
+    unsat[1] = unsat[1] || !(cm.y < Kc<float>::GAMMA);
+    // y + dt·dy stays scalar: ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with
+    // -fmad=false, which would round once instead of twice.  (dt = 0 freezes a replica.)
+    xs = make_float2(euler_clamp(xs.x, dxs.x, dt.x, Kc<float>::EPSILON, hi_s), euler_clamp(xs.y, dxs.y, dt.y, Kc<float>::EPSILON, hi_s));   // :94
+    xl = make_float2(euler_clamp(xl.x, dxl.x, dt.x, 1.0f, xl_max), euler_clamp(xl.y, dxl.y, dt.y, 1.0f, xl_max));                          // :95
+}
+
 // Asynchronous global→shared copies (LDGSTS) of the prefetch ring: no destination register and
 // no scoreboard slot, so — unlike a ring of plain loads, whose LDGs all share one of the six
 // per-warp scoreboards and therefore wait for each other — the copies really run D items ahead.
@@ -270,12 +337,22 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
                     IO::unpack(rows[i1], v[1], d[1]);
                     IO::unpack(rows[i2], v[2], d[2]);
                     IO::unpack_mem(mm, xs, xl);
+                    if constexpr (!STRICT && W == 2 && sizeof(T) == 4) {
+                        const float2 v2[3] = {make_float2(v[0][0], v[0][1]), make_float2(v[1][0], v[1][1]), make_float2(v[2][0], v[2][1])};
+                        float2 d2[3] = {make_float2(d[0][0], d[0][1]), make_float2(d[1][0], d[1][1]), make_float2(d[2][0], d[2][1])};
+                        float2 xs2 = make_float2(xs[0], xs[1]), xl2 = make_float2(xl[0], xl[1]);
+                        clause_math_f32x2(v2, d2, q, xs2, xl2, unsat, make_float2(dtw[0], dtw[1]), a.xl_max);
 #pragma unroll
-                    for (int w = 0; w < W; ++w) {
-                        const T vv[3] = {v[0][w], v[1][w], v[2][w]};
-                        T dd[3] = {d[0][w], d[1][w], d[2][w]};
-                        clause_math<T, STRICT>(vv, dd, q, xs[w], xl[w], frozen[w], unsat[w], dtw[w], a.zeta, a.xl_max);
-                        d[0][w] = dd[0]; d[1][w] = dd[1]; d[2][w] = dd[2];
+                        for (int j = 0; j < 3; ++j) { d[j][0] = d2[j].x; d[j][1] = d2[j].y; }
+                        xs[0] = xs2.x; xs[1] = xs2.y; xl[0] = xl2.x; xl[1] = xl2.y;
+                    } else {
+#pragma unroll
+                        for (int w = 0; w < W; ++w) {
+                            const T vv[3] = {v[0][w], v[1][w], v[2][w]};
+                            T dd[3] = {d[0][w], d[1][w], d[2][w]};
+                            clause_math<T, STRICT>(vv, dd, q, xs[w], xl[w], frozen[w], unsat[w], dtw[w], a.zeta, a.xl_max);
+                            d[0][w] = dd[0]; d[1][w] = dd[1]; d[2][w] = dd[2];
+                        }
                     }
                     // only the dv half changes; measured on B200, the 8-byte store (with its 2-way bank
                     // conflict across the two octets of a half-warp) beats rewriting the full row
