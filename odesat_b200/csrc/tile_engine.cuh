@@ -411,6 +411,143 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
     }
 }
 
+// ---- small-instance persistent kernel ---------------------------------------------
+// When every level of the schedule fits in one warp (≤ 32 clauses, e.g. the reference's
+// aim-100 fixtures: N = 100, M = 160) a replica tile is integrated by ONE WARP with the whole
+// state resident in shared memory: variable rows, the {xs, xl} cells and the packed clause words
+// are loaded once, the whole chunk of Euler steps runs without touching HBM, and the level
+// barriers are __syncwarp().  Same arithmetic (clause_math) and same freeze semantics as
+// k_tile_fixed.  Shared memory: rows[N] | cells[n_items][32] | entries[n_items][32] | items[n_items].
+template <typename T, bool STRICT>
+__global__ void __launch_bounds__(32) k_tile_small(const TileArgs<T> a) {
+    constexpr int W = TileTraits<T>::W;
+    using Row = typename TileTraits<T>::Row;
+    using Mem = typename TileTraits<T>::Mem;
+    using IO = RowIO<T, W>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n_items = a.n_items;
+    Row* rows = reinterpret_cast<Row*>(smem_raw);
+    Mem* cells = reinterpret_cast<Mem*>(smem_raw + (size_t)a.N * sizeof(Row));
+    uint2* entries = reinterpret_cast<uint2*>(cells + (size_t)n_items * 32);
+    uint2* s_items = entries + (size_t)n_items * 32;
+
+    const unsigned lane = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    T* vt = a.vt + tile * a.N * W;
+    Mem* mem = a.mem + tile * a.Mpad;
+    const uint2* entry = reinterpret_cast<const uint2*>(a.entry);
+
+    for (int i = lane; i < n_items; i += 32) {
+        const uint32_t it = a.items[i];
+        s_items[i] = make_uint2(it & 0xFFFFFu, ((it >> 20) & 0x7FFu) | (it & TILE_ITEM_LAST));
+    }
+    for (int i = lane; i < a.N; i += 32) {
+        T v[W], dv[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) { v[w] = vt[(int64_t)i * W + w]; dv[w] = T(0); }
+        rows[i] = IO::pack(v, dv);
+    }
+    __syncwarp();
+    for (int i = 0; i < n_items; ++i) {
+        const uint2 it = s_items[i];
+        if (lane < (it.y & 0x7FFFFFFFu)) {
+            cells[i * 32 + lane] = mem[it.x + lane];
+            entries[i * 32 + lane] = __ldg(entry + it.x + lane);
+        }
+    }
+    bool valid[W], frozen[W];
+    int32_t solved_at[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        valid[w] = tile * W + w < a.R;
+        solved_at[w] = valid[w] ? a.solved[tile * W + w] : 0;
+        frozen[w] = !valid[w] || (a.freeze && solved_at[w] >= 0);
+    }
+    __syncwarp();
+
+    for (int s = 0; s < a.nsteps; ++s) {
+        bool all_frozen = true;
+#pragma unroll
+        for (int w = 0; w < W; ++w) all_frozen = all_frozen && frozen[w];
+        if (all_frozen) break;
+        bool unsat[W];
+        T dtw[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) { unsat[w] = false; dtw[w] = (!STRICT && frozen[w]) ? T(0) : a.dt; }
+        for (int i = 0; i < n_items; ++i) {
+            const uint2 it = s_items[i];
+            if (lane < (it.y & 0x7FFFFFFFu)) {
+                const uint2 e = entries[i * 32 + lane];
+                const Mem mm = cells[i * 32 + lane];
+                const unsigned i0 = e.x & 0xFFFFu, i1 = e.x >> 16, i2 = e.y & 0xFFFFu;
+                const T q[3] = {(e.y >> 16) & 1u ? T(-1) : T(1), (e.y >> 17) & 1u ? T(-1) : T(1), (e.y >> 18) & 1u ? T(-1) : T(1)};
+                T v[3][W], d[3][W], xs[W], xl[W];
+                IO::unpack(rows[i0], v[0], d[0]);
+                IO::unpack(rows[i1], v[1], d[1]);
+                IO::unpack(rows[i2], v[2], d[2]);
+                IO::unpack_mem(mm, xs, xl);
+                if constexpr (!STRICT && W == 2 && sizeof(T) == 4) {
+                    const float2 v2[3] = {make_float2(v[0][0], v[0][1]), make_float2(v[1][0], v[1][1]), make_float2(v[2][0], v[2][1])};
+                    float2 d2[3] = {make_float2(d[0][0], d[0][1]), make_float2(d[1][0], d[1][1]), make_float2(d[2][0], d[2][1])};
+                    float2 xs2 = make_float2(xs[0], xs[1]), xl2 = make_float2(xl[0], xl[1]);
+                    clause_math_f32x2(v2, d2, q, xs2, xl2, unsat, make_float2(dtw[0], dtw[1]), a.xl_max);
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) { d[j][0] = d2[j].x; d[j][1] = d2[j].y; }
+                    xs[0] = xs2.x; xs[1] = xs2.y; xl[0] = xl2.x; xl[1] = xl2.y;
+                } else {
+#pragma unroll
+                    for (int w = 0; w < W; ++w) {
+                        const T vv[3] = {v[0][w], v[1][w], v[2][w]};
+                        T dd[3] = {d[0][w], d[1][w], d[2][w]};
+                        clause_math<T, STRICT>(vv, dd, q, xs[w], xl[w], frozen[w], unsat[w], dtw[w], a.zeta, a.xl_max);
+                        d[0][w] = dd[0]; d[1][w] = dd[1]; d[2][w] = dd[2];
+                    }
+                }
+                IO::store_dv(rows + i0, d[0]);
+                IO::store_dv(rows + i1, d[1]);
+                IO::store_dv(rows + i2, d[2]);
+                cells[i * 32 + lane] = IO::pack_mem(xs, xl);
+            }
+            if ((int)it.y < 0) __syncwarp();                // last item of a level
+        }
+        unsigned any_unsat = 0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) any_unsat |= (__any_sync(0xFFFFFFFFu, unsat[w]) ? 1u : 0u) << w;
+        for (int i = lane; i < a.N; i += 32) {
+            T v[W], dv[W];
+            IO::unpack(rows[i], v, dv);
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                if (STRICT) { if (!frozen[w]) v[w] = euler_clamp(v[w], dv[w], a.dt, T(-1), T(1)); }   // :96
+                else v[w] = euler_clamp(v[w], dv[w], dtw[w], T(-1), T(1));
+                dv[w] = T(0);
+            }
+            rows[i] = IO::pack(v, dv);
+        }
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            if (valid[w] && !frozen[w] && !((any_unsat >> w) & 1u)) {
+                if (solved_at[w] < 0) {
+                    solved_at[w] = a.step0 + s;
+                    if (lane == 0) a.solved[tile * W + w] = solved_at[w];
+                }
+                if (a.freeze) frozen[w] = true;
+            }
+        }
+        __syncwarp();
+    }
+    for (int i = lane; i < a.N; i += 32) {
+        T v[W], dv[W];
+        IO::unpack(rows[i], v, dv);
+#pragma unroll
+        for (int w = 0; w < W; ++w) vt[(int64_t)i * W + w] = v[w];
+    }
+    for (int i = 0; i < n_items; ++i) {
+        const uint2 it = s_items[i];
+        if (lane < (it.y & 0x7FFFFFFFu)) mem[it.x + lane] = cells[i * 32 + lane];
+    }
+}
+
 // canonical replica-major [row][Rp]  →  tile layouts
 template <typename T>
 __global__ void k_tile_import(const T* __restrict__ v, const T* __restrict__ xs, const T* __restrict__ xl, int64_t Rp, int64_t R,
@@ -488,10 +625,12 @@ template <typename T> struct TileEngine {
     DevBuf<Mem> mem;
     DevBuf<unsigned> oor;
     bool need_rterm = true;
+    bool small = false;   // one warp per tile, state resident in shared memory (k_tile_small)
     int nt = 512;
     int chunk = 64;   // Euler steps per launch
     int depth = 6;    // prefetch ring depth (tunable for NT = 512 only)
 
+    static size_t smem_small(int64_t N, int n_items) { return (size_t)N * 16 + (size_t)n_items * (32 * 24 + 8); }
     static bool entry_in_ring(int nt) { return nt < 1024; }
     static size_t smem_bytes(int64_t N, int n_items, int nt, int depth) {
         return (size_t)N * 16 + (size_t)nt * depth * (entry_in_ring(nt) ? 24 : 16) + (size_t)(n_items + 2) * 8;
@@ -536,6 +675,25 @@ template <typename T> struct TileEngine {
             for (int c : cand) if (v == c) nt = v;
         }
         if (const char* e = std::getenv("ODESAT_TILE_CHUNK")) { const int v = std::atoi(e); if (v > 0) chunk = v; }
+        {   // small-instance mode: every level fits in a warp and the whole tile state fits in shared memory
+            size_t maxlev = 0, items32 = 0;
+            for (const auto& b : lv->second->bucket) { maxlev = std::max(maxlev, b.size()); items32 += b.empty() ? 0 : 1; }
+            const char* e = std::getenv("ODESAT_TILE_SMALL");
+            small = maxlev <= 32 && smem_small(f.N, (int)items32 + 2) <= kMaxSmem && !(e && e[0] == '0');
+        }
+        if (small) {
+            nt = 32;
+            depth = 1;
+            const int key = (kind * 64 + 1) * 16 + 1;
+            auto it = f.tile_sched.find(key);
+            if (it == f.tile_sched.end()) it = f.tile_sched.emplace(key, build_tile_schedule(f, *lv->second, kind, 32, 1)).first;
+            sched = it->second;
+            chunk = 4096;
+            vt.alloc((size_t)(tiles * f.N * W), ledger);
+            mem.alloc((size_t)(tiles * sched->Mpad), ledger);
+            oor.alloc(1, ledger);
+            return;
+        }
         int want = 0;
         if (const char* e = std::getenv("ODESAT_TILE_D")) want = std::atoi(e);
         for (;;) {   // widest CTA first; fall back to a narrower one if its ring does not fit
@@ -604,7 +762,16 @@ template <typename T> struct TileEngine {
             default: launch<NT, 6, false>(a); break;
         }
     }
+    template <bool STRICT> void launch_small(const TileArgs<T>& a) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            ODESAT_CUDA(cudaFuncSetAttribute(k_tile_small<T, STRICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+            attr_set = true;
+        }
+        k_tile_small<T, STRICT><<<(unsigned)tiles, 32, smem_small(f.N, sched->n_items), stream>>>(a);
+    }
     void launch_nt(const TileArgs<T>& a, bool strict) {
+        if (small) { if (strict) launch_small<true>(a); else launch_small<false>(a); return; }
         if (nt == 128) launch_d<128>(a, strict);
         else if (nt == 512) launch_d<512>(a, strict);
         else if (nt == 640) launch_d<640>(a, strict);
