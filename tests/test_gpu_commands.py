@@ -1,0 +1,41 @@
+"""The reference's command bodies (main.rs:143-386) end to end on the GPU, including `solve`'s
+ratio preprocessing + trace replay (BASELINE.json configs[0]: easy.cnf via `solve -r 7`)."""
+import pytest
+
+from odesat_b200 import _lib as L
+from odesat_b200 import cnf, commands
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_render(res, original_path):
+    f = cnf.parse_dimacs_format(open(original_path).read())
+    values = {int(a): int(b) for a, b in (l.split() for l in res.rendered.splitlines())}
+    assert all(any((values.get(abs(l), 0) == 1) != (l < 0) for l in c) for c in f.clauses)
+
+
+@pytest.mark.parametrize("ratio", [None, 3.0])
+def test_solve_with_ratio_preprocessing_config0(golden_dir, tmp_path, ratio):
+    lines = []
+    out = tmp_path / "a.txt"
+    res = commands.solve(str(golden_dir / "aim100_sat.cnf"), output=str(out), ctv_ratio=ratio, step_number=200000,
+                         seed=5, log=lines.append)
+    assert res.is_satisfiable
+    assert res.n_vars < 100                                   # variables were eliminated and re-derived by the trace
+    want = ["Reading CNF formula from file...", "Parsing CNF formula...", "Preprocessing CNF formula...",
+            f"Clauses: {res.n_clauses} | Vars: {res.n_vars}", "Simulating...", "Mapping values...", "Evaluating CNF formula...",
+            "Checking if solution vector satisfies formula: true", "Rendering variable assignments...",
+            "Writing results to file..."]
+    assert lines == want
+    assert out.read_text() == res.rendered
+    _check_render(res, golden_dir / "aim100_sat.cnf")
+
+
+def test_batch_and_inter_commands(golden_dir):
+    res = commands.batch(str(golden_dir / "aim100_unsat.cnf"), 1000, 100, step_size=0.01, precision=L.F32, log=lambda s: None)
+    assert not res.is_satisfiable and res.steps == 1000 and res.winner == -1      # configs[1]
+    res = commands.inter(str(golden_dir / "aim100_sat.cnf"), 128, step_number=6000, step_size=0.01, seed=2, log=lambda s: None)
+    assert res.is_satisfiable and res.winner >= 0
+    _check_render(res, golden_dir / "aim100_sat.cnf")
+    with pytest.raises(L.OdesatError):                                            # adaptive inter (quirk Q7) is refused
+        commands.inter(str(golden_dir / "aim100_sat.cnf"), 4, step_number=10, log=lambda s: None)
