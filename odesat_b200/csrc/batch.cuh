@@ -7,6 +7,7 @@
 
 #include "formula.hpp"
 #include "kernels_gather.cuh"
+#include "tile_cluster.cuh"
 #include "tile_engine.cuh"
 
 #ifndef ODESAT_CLAUSE_HALF_VEC
@@ -71,7 +72,7 @@ template <typename T> struct BatchImpl final : BatchBase {
     DevBuf<unsigned long long> key;
     DevBuf<double> dscratch;
     // ---- tile engine state ----
-    std::unique_ptr<TileEngine<T>> tile;
+    std::unique_ptr<TileBase<T>> tile;   // TileEngine (one CTA per tile) or ClusterTileEngine (one cluster per replica)
 
     BatchImpl(const odesat_formula* f_, int64_t R_, int engine_, int schedule_) {
         f = f_;
@@ -82,20 +83,32 @@ template <typename T> struct BatchImpl final : BatchBase {
         ODESAT_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         ODESAT_CUDA(cudaEventCreate(&ev0));
         ODESAT_CUDA(cudaEventCreate(&ev1));
-        std::string why;
+        std::string why, why_c;
         const bool tile_ok = TileEngine<T>::supports(*f, R, &why);
-        if (engine_ == ODESAT_ENGINE_TILE && !tile_ok)
-            throw Error(ODESAT_EUNSUPPORTED, "tile engine cannot run this formula: " + why);
-        engine = (engine_ == ODESAT_ENGINE_TILE || (engine_ == ODESAT_ENGINE_AUTO && tile_ok && TileEngine<T>::preferred(*f, R)))
-                     ? ODESAT_ENGINE_TILE : ODESAT_ENGINE_GATHER;
+        const bool ctile_ok = ClusterTileEngine<T>::supports(*f, R, &why_c);
+        const bool force_c = ClusterTileEngine<T>::forced_cluster() != 0;
+        if (engine_ == ODESAT_ENGINE_TILE && !tile_ok && !ctile_ok)
+            throw Error(ODESAT_EUNSUPPORTED, "tile engine cannot run this formula: " + why + "; " + why_c);
+        const bool want_tile = engine_ == ODESAT_ENGINE_TILE || (engine_ == ODESAT_ENGINE_AUTO && TileEngine<T>::preferred(*f, R));
+        // Measured on B200 (N = 50 000, 2 048 replicas, f32): with 2 CTAs per replica the scattered 8-byte
+        // distributed-shared-memory gathers go through the generic LD/ST path at one lane per cycle and the
+        // step takes 12.3 ms against 7.3 ms for the general engine — so AUTO takes the cluster engine only
+        // when the rows fit in ONE CTA (no remote traffic); wider clusters on explicit request.
+        const bool c_auto = ctile_ok && ClusterTileEngine<T>::natural_cluster(*f) == 1;
+        const bool use_ctile = want_tile && ctile_ok && !tile_ok ? (force_c || engine_ == ODESAT_ENGINE_TILE || c_auto)
+                                                                 : (want_tile && ctile_ok && force_c);
+        const bool use_tile = want_tile && tile_ok && !use_ctile;
+        engine = (use_tile || use_ctile) ? ODESAT_ENGINE_TILE : ODESAT_ENGINE_GATHER;
         const int64_t N = f->N, M = f->M;
         solved.alloc((size_t)std::max<int64_t>(Rp, 1), &dev_bytes);
         dtv.alloc((size_t)std::max<int64_t>(Rp, 1), &dev_bytes);
         key.alloc(1, &dev_bytes);
         if (engine == ODESAT_ENGINE_TILE) {
-            tile.reset(new TileEngine<T>(*f, R, schedule, stream, &dev_bytes));
+            if (use_ctile) tile.reset(new ClusterTileEngine<T>(*f, R, schedule, stream, &dev_bytes));
+            else tile.reset(new TileEngine<T>(*f, R, schedule, stream, &dev_bytes));
         } else {
             S[0].alloc(N, M, Rp, &dev_bytes);   // S[1] (derivatives / adaptive ping-pong) on first use
+            pick_slab();
             unsat.alloc((size_t)std::max<int64_t>(Rp, 1), &dev_bytes);
             err.alloc((size_t)std::max<int64_t>(Rp, 1), &dev_bytes);
         }
@@ -218,17 +231,42 @@ template <typename T> struct BatchImpl final : BatchBase {
         ODESAT_CUDA(cudaStreamSynchronize(stream));
     }
 
-    GatherArgs<T> base_args(double zeta) {
+    // ---- slabs (experiment, off by default) -----------------------------------------------------
+    // ODESAT_GATHER_SLAB=S walks the batch in slabs of S replicas, `ODESAT_GATHER_SLAB_STEPS` Euler
+    // steps per visit, with ONE contribution buffer [L][S] reused by every slab, so that a slab's v
+    // rows and contributions stay in the 126 MB L2.  Measured on B200 (N = 50 000, 2 048 replicas,
+    // f32): 7.7 / 6.1 / 4.7 / 4.1 / 3.9 ms per step for S = 16 / 32 / 128 / 256 / 512 against 3.74 ms
+    // unslabbed — the small launches are instruction- and latency-bound and lose more than the L2
+    // residency gains, so the default is one launch pair over the whole batch.
+    int64_t slab = 0;        // 0 = whole batch in one launch pair
+    int slab_steps = 1;
+    void pick_slab() {
+        slab = 0;
+        slab_steps = 1;
+        const char* e = std::getenv("ODESAT_GATHER_SLAB");
+        if (!e) return;
+        const int64_t s = std::atol(e);
+        if (s <= 0 || s >= Rp || s % (16 / (int64_t)sizeof(T)) != 0 || Rp % (16 / (int64_t)sizeof(T)) != 0) return;
+        slab = s;
+        slab_steps = 8;
+        if (const char* e2 = std::getenv("ODESAT_GATHER_SLAB_STEPS")) { const int v = std::atoi(e2); if (v > 0) slab_steps = v; }
+    }
+
+    GatherArgs<T> base_args(double zeta, bool slabbed = false) {
         GatherArgs<T> a;
         a.f = f->dev;
         a.R = R;
         a.Rp = Rp;
+        a.rep0 = 0;
+        a.rep1 = R;
+        a.cstride = (slabbed && slab > 0) ? slab : Rp;
         a.zeta = (T)zeta;
         a.xl_max = T(1e4) * T(f->M);
         a.solved_step = solved.p;
         a.unsat = unsat.p;
         a.err = err.p;
-        if (contrib.n < (size_t)std::max<int64_t>(f->L * Rp, 1)) contrib.alloc((size_t)std::max<int64_t>(f->L * Rp, 1), &dev_bytes);
+        const size_t need = (size_t)std::max<int64_t>(f->L * a.cstride, 1);
+        if (contrib.n < need) contrib.alloc(need, &dev_bytes);
         a.contrib = contrib.p;
         return a;
     }
@@ -236,30 +274,42 @@ template <typename T> struct BatchImpl final : BatchBase {
     // one RHS evaluation + update = clause phase, then variable phase; 16 bytes of replicas per
     // thread when the rows are 16-byte aligned (R >= 32 ⇒ Rp is a multiple of 32)
     static constexpr int VW = 16 / (int)sizeof(T);
-    template <int V> void geom_v(int64_t rows, dim3& grid, dim3& block) const {
-        const int64_t rv = (R + V - 1) / V;
+    template <int V> void geom_v(int64_t rows, int64_t reps, int rows_per_thread, dim3& grid, dim3& block) const {
+        const int64_t rv = (reps + V - 1) / V;
         int bx = 1;
         while (bx < 256 && bx < rv) bx <<= 1;
         const int by = 256 / bx;
         block = dim3(bx, by, 1);
-        const int64_t rpb = (int64_t)by * GATHER_ROWS_PER_BLOCK;
+        const int64_t rpb = (int64_t)by * rows_per_thread;
         grid = dim3((unsigned)std::max<int64_t>((rows + rpb - 1) / rpb, 1), (unsigned)std::max<int64_t>((rv + bx - 1) / bx, 1), 1);
     }
-    template <int MODE, int V> void launch_gather_v(const GatherArgs<T>& a) {
+    template <int MODE, int V> void launch_gather_v(GatherArgs<T>& a) {
         dim3 g, b;
+        const int64_t reps = a.rep1 - a.rep0;
+        // a slab launch has few replicas: one row per thread keeps enough blocks in flight
+        a.rows_per_thread = (a.cstride != Rp) ? 1 : 8;
         if (f->M > 0) {
             // the clause phase is latency-bound on registers: half-width vectors double its occupancy
             constexpr int VC = (V > 1 && ODESAT_CLAUSE_HALF_VEC) ? V / 2 : V;
-            geom_v<VC>(f->M, g, b);
-            if (f->K == 3) k_clause_phase<T, 3, MODE, VC><<<g, b, 0, stream>>>(a);
-            else k_clause_phase<T, 0, MODE, VC><<<g, b, 0, stream>>>(a);
+            static const bool stream_on = [] { const char* e = std::getenv("ODESAT_GATHER_STREAM"); return !(e && e[0] == '0'); }();
+            if (f->K == 3 && stream_on) {
+                // streaming clause phase: RPT rows per thread, all their loads in flight as cp.async copies
+                constexpr int CB = VC * (int)sizeof(T);
+                constexpr int RPT = CB == 16 ? 2 : 4;
+                geom_v<VC>(f->M, reps, RPT, g, b);
+                k_clause_stream<T, MODE, VC, RPT><<<g, b, (size_t)RPT * 5 * 256 * CB, stream>>>(a);
+            } else {
+                geom_v<VC>(f->M, reps, a.rows_per_thread, g, b);
+                if (f->K == 3) k_clause_phase<T, 3, MODE, VC><<<g, b, 0, stream>>>(a);
+                else k_clause_phase<T, 0, MODE, VC><<<g, b, 0, stream>>>(a);
+            }
             ++launches;
         }
-        geom_v<V>(std::max<int64_t>(f->N, 1), g, b);
+        geom_v<V>(std::max<int64_t>(f->N, 1), reps, a.rows_per_thread, g, b);
         k_var_phase<T, MODE, V><<<g, b, 0, stream>>>(a);
         ++launches;
     }
-    template <int MODE> void launch_gather(const GatherArgs<T>& a) {
+    template <int MODE> void launch_gather(GatherArgs<T>& a) {
         if (R == 0) return;
         if (Rp % VW == 0 && R >= 32) launch_gather_v<MODE, VW>(a);
         else launch_gather_v<MODE, 1>(a);
@@ -288,16 +338,26 @@ template <typename T> struct BatchImpl final : BatchBase {
             return;
         }
         time_begin(ms);
-        for (int64_t i = 0; i < n; ++i) {
-            GatherArgs<T> a = base_args(zeta);   // in place: each element is read and written by its own thread
+        auto one_step = [&](int64_t r0, int64_t r1, int64_t at_step) {
+            GatherArgs<T> a = base_args(zeta, true);   // in place: each element is read and written by its own thread
+            a.rep0 = r0; a.rep1 = r1;
             a.v = S[cur].v.p; a.xs = S[cur].xs.p; a.xl = S[cur].xl.p;
             a.ov = S[cur].v.p; a.oxs = S[cur].xs.p; a.oxl = S[cur].xl.p;
             a.dt = (T)dt;
-            a.step = (int32_t)step;
+            a.step = (int32_t)at_step;
             a.freeze = freeze;
             launch_gather<G_FIXED>(a);
-            ++step;
+        };
+        if (slab > 0) {
+            for (int64_t done = 0; done < n; done += slab_steps) {
+                const int64_t k = std::min<int64_t>(slab_steps, n - done);
+                for (int64_t r0 = 0; r0 < R; r0 += slab)
+                    for (int64_t i = 0; i < k; ++i) one_step(r0, std::min<int64_t>(r0 + slab, R), step + done + i);
+            }
+        } else {
+            for (int64_t i = 0; i < n; ++i) one_step(0, R, step + i);
         }
+        step += n;
         time_end(ms);
     }
 

@@ -26,11 +26,14 @@ enum GatherMode { G_FIXED = 0, G_DERIV = 1, G_ADAPT_A = 2, G_ADAPT_B = 3 };
 template <typename T> struct GatherArgs {
     FormulaDev f;
     int64_t R = 0, Rp = 0;
+    int64_t rep0 = 0, rep1 = 0;   // replicas [rep0, rep1) of this launch (a SLAB; the whole batch when not slabbed)
+    int64_t cstride = 0;          // row stride of contrib (Rp, or the slab width: contrib[slot][rep - rep0])
+    int rows_per_thread = 8;      // rows a thread walks per launch: fewer, fatter blocks
     const T *v = nullptr, *xs = nullptr, *xl = nullptr;   // state the RHS is evaluated on
     T *ov = nullptr, *oxs = nullptr, *oxl = nullptr;      // FIXED: y(t+1) (may alias the inputs); DERIV: dy; A: y_half; B: y_new
     T *fv = nullptr, *fxs = nullptr, *fxl = nullptr;      // A: y_full (out); B: y_full (in)
     const T *yv = nullptr, *yxs = nullptr, *yxl = nullptr;   // B: the step's original y (copied through when done)
-    T* contrib = nullptr;         // [L][Rp] per-literal contributions to dv
+    T* contrib = nullptr;         // [L][cstride] per-literal contributions to dv
     T dt = T(0);
     const T* dt_arr = nullptr;    // per-replica dt (adaptive); overrides dt
     T zeta = T(0);
@@ -79,7 +82,6 @@ template <typename T, int V> __device__ __forceinline__ void vstore(T* p, const 
     }
 }
 
-constexpr int GATHER_ROWS_PER_BLOCK = 8;   // rows a thread walks per launch: fewer, fatter blocks
 
 // ---- clause phase: system.rs:41-88 for one clause and V replicas ----------------------------
 template <typename T, int K, int MODE, int V>
@@ -159,7 +161,7 @@ __device__ __forceinline__ void clause_row(const GatherArgs<T>& a, int64_t m, in
             const T r = (c[u] == val) ? T(0.5) * (q - vi.x[u]) : T(0);           // :73-77
             t.x[u] = w[u] * g + rg[u] * r;                                       // the addend of :80
         }
-        vstore<T, V>(a.contrib + (int64_t)j * Rp + rep, t);
+        vstore<T, V>(a.contrib + (int64_t)j * a.cstride + (rep - a.rep0), t);
     }
     const T hi_s = T(1) - Kc<T>::EPSILON;
     RVec<T, V> o1, o2, f1, f2;
@@ -168,7 +170,8 @@ __device__ __forceinline__ void clause_row(const GatherArgs<T>& a, int64_t m, in
         const T x = xs_m.x[u], l = xl_m.x[u];
         const T dxs = (Kc<T>::BETA * (x + Kc<T>::EPSILON)) * (c[u] - Kc<T>::GAMMA);   // :84
         const T dxl = Kc<T>::ALPHA * (c[u] - Kc<T>::DELTA);                            // :85
-        if (MODE != G_ADAPT_B && !skip[u] && !(c[u] < Kc<T>::GAMMA)) a.unsat[rep + u] = 1u;   // :88 (B's flag is discarded, :129)
+        // :88 (B's flag is discarded, :129); raised only, so a stale cached 1 just skips the store
+        if (MODE != G_ADAPT_B && !skip[u] && !(c[u] < Kc<T>::GAMMA) && a.unsat[rep + u] == 0u) a.unsat[rep + u] = 1u;
         if (MODE == G_FIXED) {
             o1.x[u] = skip[u] ? x : euler_clamp(x, dxs, dt[u], Kc<T>::EPSILON, hi_s);  // :94
             o2.x[u] = skip[u] ? l : euler_clamp(l, dxl, dt[u], T(1), a.xl_max);        // :95
@@ -207,12 +210,186 @@ __device__ __forceinline__ void clause_row(const GatherArgs<T>& a, int64_t m, in
 
 template <typename T, int K, int MODE, int V>
 __global__ void __launch_bounds__(256) k_clause_phase(const GatherArgs<T> a) {
-    const int64_t rep = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * V;
-    if (rep >= a.R) return;
+    const int64_t rep = a.rep0 + ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * V;
+    if (rep >= a.rep1) return;
 #pragma unroll 2
-    for (int it = 0; it < GATHER_ROWS_PER_BLOCK; ++it) {
-        const int64_t m = ((int64_t)blockIdx.x * GATHER_ROWS_PER_BLOCK + it) * blockDim.y + threadIdx.y;
+    for (int it = 0; it < a.rows_per_thread; ++it) {
+        const int64_t m = ((int64_t)blockIdx.x * a.rows_per_thread + it) * blockDim.y + threadIdx.y;
         if (m < a.f.M) clause_row<T, K, MODE, V>(a, m, rep);
+    }
+}
+
+// ---- streaming clause phase (uniform 3-literal clauses) -------------------------------------------
+// The plain kernel above is latency-bound: literal load → v gather → memory load are three
+// dependent round trips per row (ncu: long-scoreboard stalls 16–17 cycles per issued instruction,
+// 24 % of DRAM peak).  Here a thread owns RPT rows; it first loads the literals of all of them, then
+// issues every state load of all of them — 3 v rows, xs, xl per row — as cp.async copies into its own
+// shared-memory cells (no destination registers, so the loads of all RPT rows are in flight
+// together), and only then computes row by row as the copy groups land.  Two round trips per RPT rows
+// instead of three per row.  Same arithmetic, statement for statement, as clause_row.
+template <int BYTES> __device__ __forceinline__ void cp_async_n(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+    else if (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_g() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {   // wait until at most n groups are pending
+    switch (n) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    }
+}
+
+template <typename T, int MODE, int V, int RPT>
+__global__ void __launch_bounds__(256) k_clause_stream(const GatherArgs<T> a) {
+    static_assert(RPT >= 1 && RPT <= 4, "cp_async_wait_dyn covers up to 4 groups");
+    constexpr int CB = V * (int)sizeof(T);                       // bytes of one cell (V replicas of one row)
+    extern __shared__ __align__(16) unsigned char stream_smem[];
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    auto cell = [&](int r, int c) { return stream_smem + ((size_t)(r * 5 + c) * 256 + tid) * CB; };
+    const int64_t Rp = a.Rp;
+    const int64_t rep = a.rep0 + ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * V;
+    const bool rep_ok = rep < a.rep1;
+
+    bool skip[V];   // element is frozen / done / beyond R: keep (or pass through) its state
+    bool all_skip = true;
+    T dt[V];
+#pragma unroll
+    for (int u = 0; u < V; ++u) {
+        const bool in = rep_ok && rep + u < a.R;
+        bool sk = !in;
+        if (in) {
+            if (MODE == G_FIXED) sk = a.freeze && a.solved_step[rep + u] >= 0;
+            else if (MODE == G_ADAPT_A) sk = a.solved_step[rep + u] >= 0;
+            else if (MODE == G_ADAPT_B) sk = a.solved_step[rep + u] >= 0 || a.unsat[rep + u] == 0u;
+        }
+        skip[u] = sk;
+        all_skip = all_skip && sk;
+        dt[u] = (a.dt_arr && rep_ok) ? a.dt_arr[rep + u < a.R ? rep + u : rep] : a.dt;
+    }
+    int lit[RPT][3];
+    int64_t mrow[RPT];
+    bool ok[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        mrow[r] = ((int64_t)blockIdx.x * RPT + r) * blockDim.y + threadIdx.y;
+        ok[r] = rep_ok && mrow[r] < a.f.M;
+        if (ok[r] && !all_skip) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) lit[r][j] = __ldg(a.f.lits + mrow[r] * 3 + j);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        if (ok[r] && !all_skip) {
+            const int64_t at = mrow[r] * Rp + rep;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int var = (lit[r][j] < 0 ? -lit[r][j] : lit[r][j]) - 1;
+                cp_async_n<CB>(cell(r, j), a.v + (int64_t)var * Rp + rep);
+            }
+            cp_async_n<CB>(cell(r, 3), a.xs + at);
+            cp_async_n<CB>(cell(r, 4), a.xl + at);
+        }
+        cp_async_commit_g();
+    }
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        cp_async_wait_dyn(RPT - 1 - r);
+        if (!ok[r]) continue;
+        const int64_t at = mrow[r] * Rp + rep;
+        if (all_skip) {
+            if (MODE == G_ADAPT_B) {   // done / just flagged: state untouched (system.rs:122)
+                vstore<T, V>(a.oxs + at, vload<T, V>(a.yxs + at));
+                vstore<T, V>(a.oxl + at, vload<T, V>(a.yxl + at));
+            }
+            continue;
+        }
+        RVec<T, V> vis[3], xs_m, xl_m;
+        T qs[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            vis[j] = *reinterpret_cast<const RVec<T, V>*>(cell(r, j));
+            qs[j] = lit[r][j] < 0 ? T(-1) : T(1);
+        }
+        xs_m = *reinterpret_cast<const RVec<T, V>*>(cell(r, 3));
+        xl_m = *reinterpret_cast<const RVec<T, V>*>(cell(r, 4));
+        T mn[V], sm[V];
+#pragma unroll
+        for (int u = 0; u < V; ++u) { mn[u] = inf_v<T>(); sm[u] = inf_v<T>(); }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {                              // :46-57
+#pragma unroll
+            for (int u = 0; u < V; ++u) {
+                const T val = T(1) - qs[j] * vis[j].x[u];          // :49
+                if (val < mn[u]) { sm[u] = mn[u]; mn[u] = val; }   // :50-52
+                else if (val < sm[u]) { sm[u] = val; }             // :53-55
+            }
+        }
+        T c[V], w[V], rg[V];
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+            c[u] = T(0.5) * mn[u];                                 // :60
+            w[u] = xl_m.x[u] * xs_m.x[u];
+            rg[u] = (T(1) + a.zeta * xl_m.x[u]) * (T(1) - xs_m.x[u]);
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {                              // :62-81
+            RVec<T, V> t;
+#pragma unroll
+            for (int u = 0; u < V; ++u) {
+                const T val = T(1) - qs[j] * vis[j].x[u];
+                const T g = (T(0.5) * qs[j]) * ((val != mn[u]) ? mn[u] : sm[u]);       // :64-70
+                const T rr = (c[u] == val) ? T(0.5) * (qs[j] - vis[j].x[u]) : T(0);    // :73-77
+                t.x[u] = w[u] * g + rg[u] * rr;                                        // the addend of :80
+            }
+            vstore<T, V>(a.contrib + (mrow[r] * 3 + j) * a.cstride + (rep - a.rep0), t);
+        }
+        const T hi_s = T(1) - Kc<T>::EPSILON;
+        RVec<T, V> o1, o2, f1, f2;
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+            const T x = xs_m.x[u], l = xl_m.x[u];
+            const T dxs = (Kc<T>::BETA * (x + Kc<T>::EPSILON)) * (c[u] - Kc<T>::GAMMA);   // :84
+            const T dxl = Kc<T>::ALPHA * (c[u] - Kc<T>::DELTA);                            // :85
+            // :88 (B's flag is discarded, :129); the flag is only ever raised, so a stale cached 1 just skips the store
+            if (MODE != G_ADAPT_B && !skip[u] && !(c[u] < Kc<T>::GAMMA) && a.unsat[rep + u] == 0u) a.unsat[rep + u] = 1u;
+            if (MODE == G_FIXED) {
+                o1.x[u] = skip[u] ? x : euler_clamp(x, dxs, dt[u], Kc<T>::EPSILON, hi_s);  // :94
+                o2.x[u] = skip[u] ? l : euler_clamp(l, dxl, dt[u], T(1), a.xl_max);        // :95
+            } else if (MODE == G_DERIV) {
+                o1.x[u] = dxs;
+                o2.x[u] = dxl;
+            } else if (MODE == G_ADAPT_A) {
+                const T h = T(0.5) * dt[u];
+                o1.x[u] = euler_clamp(x, dxs, h, Kc<T>::EPSILON, hi_s);                    // :128
+                o2.x[u] = euler_clamp(l, dxl, h, T(1), a.xl_max);
+                f1.x[u] = euler_clamp(x, dxs, dt[u], Kc<T>::EPSILON, hi_s);                // :125
+                f2.x[u] = euler_clamp(l, dxl, dt[u], T(1), a.xl_max);
+            } else {
+                const T h = T(0.5) * dt[u];
+                o1.x[u] = euler_clamp(x, dxs, h, Kc<T>::EPSILON, hi_s);                    // :130
+                o2.x[u] = euler_clamp(l, dxl, h, T(1), a.xl_max);
+            }
+        }
+        if (MODE == G_ADAPT_A) {
+            vstore<T, V>(a.fxs + at, f1);
+            vstore<T, V>(a.fxl + at, f2);
+        }
+        if (MODE == G_ADAPT_B) {
+            const RVec<T, V> yx = vload<T, V>(a.yxs + at), yl = vload<T, V>(a.yxl + at);
+            const RVec<T, V> fx = vload<T, V>(a.fxs + at), fl = vload<T, V>(a.fxl + at);
+#pragma unroll
+            for (int u = 0; u < V; ++u) {
+                if (skip[u]) { o1.x[u] = yx.x[u]; o2.x[u] = yl.x[u]; }
+                else if (rep + u < a.R) err_max<T>(a.err + rep + u, rmax(fabs(fx.x[u] - o1.x[u]), fabs(fl.x[u] - o2.x[u])));   // :104-107
+            }
+        }
+        vstore<T, V>(a.oxs + at, o1);
+        vstore<T, V>(a.oxl + at, o2);
     }
 }
 
@@ -257,7 +434,7 @@ __device__ __forceinline__ void var_row(const GatherArgs<T>& a, int64_t row, int
         RVec<T, V> t[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if (e + k < e1) t[k] = vload_rw<T, V>(a.contrib + (int64_t)__ldg(a.f.occ_slot + e + k) * Rp + rep);
+            if (e + k < e1) t[k] = vload_rw<T, V>(a.contrib + (int64_t)__ldg(a.f.occ_slot + e + k) * a.cstride + (rep - a.rep0));
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             if (e + k < e1) {
@@ -297,11 +474,11 @@ __device__ __forceinline__ void var_row(const GatherArgs<T>& a, int64_t row, int
 
 template <typename T, int MODE, int V>
 __global__ void __launch_bounds__(256) k_var_phase(const GatherArgs<T> a) {
-    const int64_t rep = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * V;
-    if (rep >= a.R) return;
+    const int64_t rep = a.rep0 + ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * V;
+    if (rep >= a.rep1) return;
     const int64_t rows = a.f.N > 0 ? a.f.N : 1;
-    for (int it = 0; it < GATHER_ROWS_PER_BLOCK; ++it) {
-        const int64_t row = ((int64_t)blockIdx.x * GATHER_ROWS_PER_BLOCK + it) * blockDim.y + threadIdx.y;
+    for (int it = 0; it < a.rows_per_thread; ++it) {
+        const int64_t row = ((int64_t)blockIdx.x * a.rows_per_thread + it) * blockDim.y + threadIdx.y;
         if (row < rows) var_row<T, MODE, V>(a, row, rep);
     }
 }

@@ -612,7 +612,17 @@ __global__ void k_tile_export(T* __restrict__ v, T* __restrict__ xs, T* __restri
     }
 }
 
-template <typename T> struct TileEngine {
+// What BatchImpl needs from a shared-memory-resident engine (k_tile_fixed / k_tile_small here,
+// the thread-block-cluster variant in tile_cluster.cuh).
+template <typename T> struct TileBase {
+    virtual ~TileBase() = default;
+    virtual void reset_control() = 0;
+    virtual int64_t import_state(const T* v, const T* xs, const T* xl, int64_t Rp) = 0;   // canonical [row][Rp] → tile layout
+    virtual int64_t export_state(T* v, T* xs, T* xl, int64_t Rp) = 0;
+    virtual int64_t run_fixed(T dt, T zeta, int64_t n, int freeze, int32_t* solved, int64_t step0) = 0;   // → launches
+};
+
+template <typename T> struct TileEngine final : TileBase<T> {
     static constexpr int W = TileTraits<T>::W;
     using Mem = typename TileTraits<T>::Mem;
     static constexpr size_t kMaxSmem = 232448 - 1024;   // 227 KB opt-in limit minus static slack
@@ -713,7 +723,7 @@ template <typename T> struct TileEngine {
         mem.alloc((size_t)(tiles * sched->Mpad), ledger);
         oor.alloc(1, ledger);
     }
-    void reset_control() { need_rterm = true; }
+    void reset_control() override { need_rterm = true; }
 
     void geom(int64_t rows, dim3& grid, dim3& block) const {
         int bx = 1;
@@ -723,7 +733,7 @@ template <typename T> struct TileEngine {
         grid = dim3((unsigned)((rows + by - 1) / by), (unsigned)((tiles + bx - 1) / bx), 1);
     }
 
-    int64_t import_state(const T* v, const T* xs, const T* xl, int64_t Rp) {
+    int64_t import_state(const T* v, const T* xs, const T* xl, int64_t Rp) override {
         ODESAT_CUDA(cudaMemsetAsync(oor.p, 0, 4, stream));
         dim3 g, b;
         geom(f.N + sched->Mpad, g, b);
@@ -735,7 +745,7 @@ template <typename T> struct TileEngine {
         need_rterm = h != 0;
         return 1;
     }
-    int64_t export_state(T* v, T* xs, T* xl, int64_t Rp) {
+    int64_t export_state(T* v, T* xs, T* xl, int64_t Rp) override {
         dim3 g, b;
         geom(f.N + sched->Mpad, g, b);
         k_tile_export<T><<<g, b, 0, stream>>>(v, xs, xl, Rp, R, f.N, sched->Mpad, sched->d_perm.p, vt.p, mem.p, tiles);
@@ -779,7 +789,7 @@ template <typename T> struct TileEngine {
         else launch_d<1024>(a, strict);
     }
 
-    int64_t run_fixed(T dt, T zeta, int64_t n, int freeze, int32_t* solved, int64_t step0) {
+    int64_t run_fixed(T dt, T zeta, int64_t n, int freeze, int32_t* solved, int64_t step0) override {
         int64_t launches = 0;
         const bool zeta_ok = std::isfinite((double)zeta);
         for (int64_t done = 0; done < n;) {

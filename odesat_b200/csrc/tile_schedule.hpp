@@ -42,12 +42,14 @@ struct TileSchedule {
     int64_t M = 0, Mpad = 0;           // real clauses, slots (levels padded to 8 slots = 128 B)
     int nlev = 0;
     int n_items = 0;
-    std::vector<uint32_t> items;       // [n_items] packed (base, nvalid, last)
+    std::vector<uint32_t> items;       // [n_items] packed (base, nvalid, last) — valid when nt <= 1024 and Mpad < 2^20
+    std::vector<uint2> items2;         // [n_items] {base, nvalid | last << 31} — any width (cluster tiles)
     std::vector<int32_t> perm;         // [Mpad] slot → clause index, −1 = padding
     std::vector<uint64_t> entry;       // [Mpad] packed clause: 3×16-bit row + sign bits + valid
     double conflict_wavefronts = 0;    // avg shared-memory wavefronts per quarter-warp access (1 = ideal)
     DevBuf<int32_t> d_perm;
     DevBuf<uint32_t> d_items;
+    DevBuf<uint2> d_items2;
     DevBuf<uint64_t> d_entry;
 };
 
@@ -166,7 +168,9 @@ struct TileLevels {
     std::vector<std::vector<int32_t>> bucket;   // clauses of each level, ascending index
 };
 
-inline std::shared_ptr<TileLevels> build_tile_levels(const odesat_formula& f, int kind) {
+// BALANCED: `target` = clauses per level aimed for, `round` = the item width the class capacity is
+// rounded up to (a level is a whole number of items wherever possible).
+inline std::shared_ptr<TileLevels> build_tile_levels(const odesat_formula& f, int kind, int target = 1024, int round = 512) {
     auto s = std::make_shared<TileLevels>();
     const int64_t M = f.M, N = f.N;
     std::vector<int32_t> level(M, 0);
@@ -187,8 +191,8 @@ inline std::shared_ptr<TileLevels> build_tile_levels(const odesat_formula& f, in
     } else {
         // target: levels of 1024 clauses (a whole number of 512-thread items), but never fewer
         // colours than the max variable degree; classes are capped at a multiple of 512
-        int C = (int)std::max<int64_t>(f.max_degree + 2, (M + 1023) / 1024);
-        const int cap = (int)(((M + C - 1) / C + 511) / 512 * 512);
+        int C = (int)std::max<int64_t>(f.max_degree + 2, (M + target - 1) / target);
+        const int cap = (int)(((M + C - 1) / C + round - 1) / round * round);
 
         std::vector<std::vector<uint64_t>> usedc;   // per variable: bitset of colours taken
         int words = (C + 63 + 64) / 64;             // slack for overflow colours
@@ -249,22 +253,29 @@ inline std::shared_ptr<TileSchedule> build_tile_schedule(const odesat_formula& f
         while (s->perm.size() % 8) { s->perm.push_back(-1); s->entry.push_back(0); }   // 128-byte aligned level start
         for (size_t o = 0; o < n; o += (size_t)nt) {
             const size_t cnt = std::min<size_t>((size_t)nt, n - o);
-            s->items.push_back(pack_item((uint32_t)(base0 + o), (uint32_t)cnt, o + (size_t)nt >= n));
+            const bool last = o + (size_t)nt >= n;
+            s->items.push_back(pack_item((uint32_t)((base0 + o) & 0xFFFFFu), (uint32_t)(cnt & 0x7FFu), last));
+            s->items2.push_back(make_uint2((uint32_t)(base0 + o), (uint32_t)cnt | (last ? TILE_ITEM_LAST : 0u)));
         }
         ++s->nlev;
     }
     const size_t pad = (size_t)((depth % 2) ? 2 * depth : depth);   // the strict first-step kernel uses a ring of 2
-    while (s->items.size() % pad || s->items.size() <= (size_t)depth) s->items.push_back(pack_item(0, 0, false));
+    while (s->items.size() % pad || s->items.size() <= (size_t)depth) {
+        s->items.push_back(pack_item(0, 0, false));
+        s->items2.push_back(make_uint2(0u, 0u));
+    }
     s->Mpad = (int64_t)s->perm.size();
-    if (s->Mpad >= (1 << 20)) throw Error(ODESAT_EUNSUPPORTED, "tile schedule: more than 2^20 clause slots");
+    if (nt <= 1024 && s->Mpad >= (1 << 20)) throw Error(ODESAT_EUNSUPPORTED, "tile schedule: more than 2^20 clause slots");
     s->n_items = (int)s->items.size();
     s->conflict_wavefronts = wcnt ? wsum / wcnt : 1.0;
     if (!upload) return s;
     s->d_items.alloc(std::max<size_t>(s->items.size(), 1));
+    s->d_items2.alloc(std::max<size_t>(s->items2.size(), 1));
     s->d_perm.alloc(std::max<size_t>(s->perm.size(), 1));
     s->d_entry.alloc(std::max<size_t>(s->entry.size(), 1));
     if (!s->perm.empty()) {
         ODESAT_CUDA(cudaMemcpy(s->d_items.p, s->items.data(), s->items.size() * 4, cudaMemcpyHostToDevice));
+        ODESAT_CUDA(cudaMemcpy(s->d_items2.p, s->items2.data(), s->items2.size() * 8, cudaMemcpyHostToDevice));
         ODESAT_CUDA(cudaMemcpy(s->d_perm.p, s->perm.data(), s->perm.size() * 4, cudaMemcpyHostToDevice));
         ODESAT_CUDA(cudaMemcpy(s->d_entry.p, s->entry.data(), s->entry.size() * 8, cudaMemcpyHostToDevice));
     }
