@@ -360,7 +360,7 @@ template <typename T> struct ClusterTileEngine final : TileBase<T> {
         if (want_d >= 2 && want_d <= depth) depth = want_d;
         const int key = 1 << 24 | ((kind * 64 + width / 32) * 16 + depth);
         auto it = f.tile_sched.find(key);
-        if (it == f.tile_sched.end()) it = f.tile_sched.emplace(key, build_tile_schedule(f, *lv->second, kind, width, depth)).first;
+        if (it == f.tile_sched.end()) it = f.tile_sched.emplace(key, build_tile_schedule(f, *lv->second, kind, width, depth, /*upload=*/true, /*wide=*/true)).first;
         sched = it->second;
         if (smem_bytes(f.N, sched->n_items, cl, nt, depth) > kMaxSmem) throw Error(ODESAT_EUNSUPPORTED, "schedule does not fit in shared memory");
         vt.alloc((size_t)(R * f.N), ledger);

@@ -175,7 +175,7 @@ __device__ __forceinline__ float2 bc2(float x) { return make_float2(x, x); }
 // Fast path of clause_math for the two f32 replicas of a tile at once (same operations in the same
 // order as clause_math<float, false>, the add / mul / fma ones packed).
 __device__ __forceinline__ void clause_math_f32x2(const float2 (&v)[3], float2 (&d)[3], const float (&q)[3], float2& xs, float2& xl,
-                                                  bool (&unsat)[2], float2 dt, float xl_max) {
+                                                  float (&mx)[2], float2 dt, float xl_max) {
     const float hi_s = 1.0f - Kc<float>::EPSILON;
     float2 a[3];
 #pragma unroll
@@ -200,12 +200,16 @@ __device__ __forceinline__ void clause_math_f32x2(const float2 (&v)[3], float2 (
     }
     const float2 dxs = mul2(mul2(bc2(Kc<float>::BETA), add2(xs, bc2(Kc<float>::EPSILON))), add2(cm, bc2(-Kc<float>::GAMMA)));   // :84
     const float2 dxl = mul2(bc2(Kc<float>::ALPHA), add2(cm, bc2(-Kc<float>::DELTA)));                                           // :85
-    unsat[0] = unsat[0] || !(cm.x < Kc<float>::GAMMA);                      // :88
-    unsat[1] = unsat[1] || !(cm.y < Kc<float>::GAMMA);
-    // y + dt·dy stays scalar: ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with
-    // -fmad=false, which would round once instead of twice.  (dt = 0 freezes a replica.)
-    xs = make_float2(euler_clamp(xs.x, dxs.x, dt.x, Kc<float>::EPSILON, hi_s), euler_clamp(xs.y, dxs.y, dt.y, Kc<float>::EPSILON, hi_s));   // :94
-    xl = make_float2(euler_clamp(xl.x, dxl.x, dt.x, 1.0f, xl_max), euler_clamp(xl.y, dxl.y, dt.y, 1.0f, xl_max));                          // :95
+    // :88 as a running maximum: C_m = 0.5·min exactly (the minimum is 0 or a multiple of 2^-24 ≥ 2^-24), so
+    // "some C_m ≥ 0.25" ⇔ "max over clauses of min ≥ 0.5"; no NaN can occur on this path
+    mx[0] = rmax(mx[0], mn.x);
+    mx[1] = rmax(mx[1], mn.y);
+    // y + dt·dy: the products are packed, the additions stay scalar — ptxas (12.9) contracts
+    // mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with -fmad=false, which would round once instead
+    // of twice.  (dt = 0 freezes a replica.)
+    const float2 pxs = mul2(dt, dxs), pxl = mul2(dt, dxl);
+    xs = make_float2(rmin(rmax(__fadd_rn(xs.x, pxs.x), Kc<float>::EPSILON), hi_s), rmin(rmax(__fadd_rn(xs.y, pxs.y), Kc<float>::EPSILON), hi_s));   // :94
+    xl = make_float2(rmin(rmax(__fadd_rn(xl.x, pxl.x), 1.0f), xl_max), rmin(rmax(__fadd_rn(xl.y, pxl.y), 1.0f), xl_max));                          // :95
 }
 
 // Asynchronous global→shared copies (LDGSTS) of the prefetch ring: no destination register and
@@ -310,9 +314,14 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
         for (int w = 0; w < W; ++w) all_frozen = all_frozen && frozen[w];
         if (all_frozen) break;
         bool unsat[W];
+        float mx[2] = {0.0f, 0.0f};   // f32x2 fast path: running max of the clause minima (→ unsat after the clause phase)
         T dtw[W];   // per-replica step: 0 freezes a replica without a branch (fast path only)
 #pragma unroll
         for (int w = 0; w < W; ++w) { unsat[w] = false; dtw[w] = (!STRICT && frozen[w]) ? T(0) : a.dt; }
+        if constexpr (sizeof(T) == 4) {   // keep the per-replica dt in registers (ptxas otherwise rebuilds it in every item)
+#pragma unroll
+            for (int w = 0; w < W; ++w) asm volatile("" : "+f"(dtw[w]));
+        }
         // ------------------------------ clause phase -----------------------------------
         for (int base = 0; base < n_items; base += D) {
 #pragma unroll
@@ -330,18 +339,21 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
                 if (ER && mine) e = my_cell_e[k * NT];
                 if (mine) {
                     const Mem mm = my_cell_m[k * NT];
-                    const unsigned i0 = e.x & 0xFFFFu, i1 = e.x >> 16, i2 = e.y & 0xFFFFu;
-                    const T q[3] = {(e.y >> 16) & 1u ? T(-1) : T(1), (e.y >> 17) & 1u ? T(-1) : T(1), (e.y >> 18) & 1u ? T(-1) : T(1)};
+                    // byte offsets of the three rows (pre-shifted in the packed clause), signs in the top byte
+                    Row* const r0 = reinterpret_cast<Row*>(smem_raw + (e.x & 0x3FFF0u));
+                    Row* const r1 = reinterpret_cast<Row*>(smem_raw + ((e.x >> 14) & 0x3FFF0u));
+                    Row* const r2 = reinterpret_cast<Row*>(smem_raw + (e.y & 0x3FFF0u));
+                    const T q[3] = {(e.y >> 24) & 1u ? T(-1) : T(1), (e.y >> 25) & 1u ? T(-1) : T(1), (e.y >> 26) & 1u ? T(-1) : T(1)};
                     T v[3][W], d[3][W], xs[W], xl[W];
-                    IO::unpack(rows[i0], v[0], d[0]);
-                    IO::unpack(rows[i1], v[1], d[1]);
-                    IO::unpack(rows[i2], v[2], d[2]);
+                    IO::unpack(*r0, v[0], d[0]);
+                    IO::unpack(*r1, v[1], d[1]);
+                    IO::unpack(*r2, v[2], d[2]);
                     IO::unpack_mem(mm, xs, xl);
                     if constexpr (!STRICT && W == 2 && sizeof(T) == 4) {
                         const float2 v2[3] = {make_float2(v[0][0], v[0][1]), make_float2(v[1][0], v[1][1]), make_float2(v[2][0], v[2][1])};
                         float2 d2[3] = {make_float2(d[0][0], d[0][1]), make_float2(d[1][0], d[1][1]), make_float2(d[2][0], d[2][1])};
                         float2 xs2 = make_float2(xs[0], xs[1]), xl2 = make_float2(xl[0], xl[1]);
-                        clause_math_f32x2(v2, d2, q, xs2, xl2, unsat, make_float2(dtw[0], dtw[1]), a.xl_max);
+                        clause_math_f32x2(v2, d2, q, xs2, xl2, mx, make_float2(dtw[0], dtw[1]), a.xl_max);
 #pragma unroll
                         for (int j = 0; j < 3; ++j) { d[j][0] = d2[j].x; d[j][1] = d2[j].y; }
                         xs[0] = xs2.x; xs[1] = xs2.y; xl[0] = xl2.x; xl[1] = xl2.y;
@@ -356,9 +368,9 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
                     }
                     // only the dv half changes; measured on B200, the 8-byte store (with its 2-way bank
                     // conflict across the two octets of a half-warp) beats rewriting the full row
-                    IO::store_dv(rows + i0, d[0]);
-                    IO::store_dv(rows + i1, d[1]);
-                    IO::store_dv(rows + i2, d[2]);
+                    IO::store_dv(r0, d[0]);
+                    IO::store_dv(r1, d[1]);
+                    IO::store_dv(r2, d[2]);
                     __stcg(at16(my_mem, it.x), IO::pack_mem(xs, xl));
                 }
                 {   // refill cell k with item i + D (next step's item i + D − n_items at the end)
@@ -375,6 +387,7 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
             }
         }
         // ------------------------------ flags + variable phase ---------------------------
+        if constexpr (!STRICT && W == 2 && sizeof(T) == 4) { unsat[0] = !(mx[0] < 0.5f); unsat[1] = !(mx[1] < 0.5f); }
         unsigned any_unsat = 0;   // __syncthreads_or is a boolean OR: one call per replica of the tile
 #pragma unroll
         for (int w = 0; w < W; ++w) any_unsat |= (__syncthreads_or((int)unsat[w]) ? 1u : 0u) << w;
@@ -471,6 +484,7 @@ __global__ void __launch_bounds__(32) k_tile_small(const TileArgs<T> a) {
         for (int w = 0; w < W; ++w) all_frozen = all_frozen && frozen[w];
         if (all_frozen) break;
         bool unsat[W];
+        float mx[2] = {0.0f, 0.0f};
         T dtw[W];
 #pragma unroll
         for (int w = 0; w < W; ++w) { unsat[w] = false; dtw[w] = (!STRICT && frozen[w]) ? T(0) : a.dt; }
@@ -479,18 +493,20 @@ __global__ void __launch_bounds__(32) k_tile_small(const TileArgs<T> a) {
             if (lane < (it.y & 0x7FFFFFFFu)) {
                 const uint2 e = entries[i * 32 + lane];
                 const Mem mm = cells[i * 32 + lane];
-                const unsigned i0 = e.x & 0xFFFFu, i1 = e.x >> 16, i2 = e.y & 0xFFFFu;
-                const T q[3] = {(e.y >> 16) & 1u ? T(-1) : T(1), (e.y >> 17) & 1u ? T(-1) : T(1), (e.y >> 18) & 1u ? T(-1) : T(1)};
+                Row* const r0 = reinterpret_cast<Row*>(smem_raw + (e.x & 0x3FFF0u));
+                Row* const r1 = reinterpret_cast<Row*>(smem_raw + ((e.x >> 14) & 0x3FFF0u));
+                Row* const r2 = reinterpret_cast<Row*>(smem_raw + (e.y & 0x3FFF0u));
+                const T q[3] = {(e.y >> 24) & 1u ? T(-1) : T(1), (e.y >> 25) & 1u ? T(-1) : T(1), (e.y >> 26) & 1u ? T(-1) : T(1)};
                 T v[3][W], d[3][W], xs[W], xl[W];
-                IO::unpack(rows[i0], v[0], d[0]);
-                IO::unpack(rows[i1], v[1], d[1]);
-                IO::unpack(rows[i2], v[2], d[2]);
+                IO::unpack(*r0, v[0], d[0]);
+                IO::unpack(*r1, v[1], d[1]);
+                IO::unpack(*r2, v[2], d[2]);
                 IO::unpack_mem(mm, xs, xl);
                 if constexpr (!STRICT && W == 2 && sizeof(T) == 4) {
                     const float2 v2[3] = {make_float2(v[0][0], v[0][1]), make_float2(v[1][0], v[1][1]), make_float2(v[2][0], v[2][1])};
                     float2 d2[3] = {make_float2(d[0][0], d[0][1]), make_float2(d[1][0], d[1][1]), make_float2(d[2][0], d[2][1])};
                     float2 xs2 = make_float2(xs[0], xs[1]), xl2 = make_float2(xl[0], xl[1]);
-                    clause_math_f32x2(v2, d2, q, xs2, xl2, unsat, make_float2(dtw[0], dtw[1]), a.xl_max);
+                    clause_math_f32x2(v2, d2, q, xs2, xl2, mx, make_float2(dtw[0], dtw[1]), a.xl_max);
 #pragma unroll
                     for (int j = 0; j < 3; ++j) { d[j][0] = d2[j].x; d[j][1] = d2[j].y; }
                     xs[0] = xs2.x; xs[1] = xs2.y; xl[0] = xl2.x; xl[1] = xl2.y;
@@ -503,13 +519,14 @@ __global__ void __launch_bounds__(32) k_tile_small(const TileArgs<T> a) {
                         d[0][w] = dd[0]; d[1][w] = dd[1]; d[2][w] = dd[2];
                     }
                 }
-                IO::store_dv(rows + i0, d[0]);
-                IO::store_dv(rows + i1, d[1]);
-                IO::store_dv(rows + i2, d[2]);
+                IO::store_dv(r0, d[0]);
+                IO::store_dv(r1, d[1]);
+                IO::store_dv(r2, d[2]);
                 cells[i * 32 + lane] = IO::pack_mem(xs, xl);
             }
             if ((int)it.y < 0) __syncwarp();                // last item of a level
         }
+        if constexpr (!STRICT && W == 2 && sizeof(T) == 4) { unsat[0] = !(mx[0] < 0.5f); unsat[1] = !(mx[1] < 0.5f); }
         unsigned any_unsat = 0;
 #pragma unroll
         for (int w = 0; w < W; ++w) any_unsat |= (__any_sync(0xFFFFFFFFu, unsat[w]) ? 1u : 0u) << w;
@@ -657,7 +674,7 @@ template <typename T> struct TileEngine final : TileBase<T> {
         if (R < 1) return no("empty batch");
         if (f.K != 3) return no("needs uniform clause length 3");
         if (!f.distinct_vars) return no("a clause repeats a variable");
-        if (f.N > 65535) return no("more than 65535 variables");
+        if (f.N > 16383) return no("more than 16383 variables");
         if (pick_depth(f.N, 128, 4096) < 2) return no("variables do not fit in 227 KB of shared memory");
         return true;
     }

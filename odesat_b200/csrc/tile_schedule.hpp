@@ -55,13 +55,22 @@ struct TileSchedule {
 
 constexpr uint64_t TILE_VALID_BIT = 1ull << 51;
 
-inline uint64_t pack_entry3(const int32_t* var, const bool* neg) {
-    uint64_t e = TILE_VALID_BIT;
-    for (int j = 0; j < 3; ++j) {
-        e |= (uint64_t)(uint16_t)var[j] << (16 * j);
-        if (neg[j]) e |= 1ull << (48 + j);
+// wide = false: the tile kernels' form — BYTE OFFSETS of the three 16-byte rows, pre-shifted so that each is one
+//   mask (or shift + mask) away: lo = off0 | off1 << 14, hi = off2 | signs << 24 (off = var·16, var < 2^14)
+// wide = true:  three 16-bit variable indices + sign bits at 48..50 (cluster kernel, up to 65 535 variables)
+inline uint64_t pack_entry3(const int32_t* var, const bool* neg, bool wide) {
+    if (wide) {
+        uint64_t e = TILE_VALID_BIT;
+        for (int j = 0; j < 3; ++j) {
+            e |= (uint64_t)(uint16_t)var[j] << (16 * j);
+            if (neg[j]) e |= 1ull << (48 + j);
+        }
+        return e;
     }
-    return e;
+    const uint32_t lo = ((uint32_t)var[0] << 4) | ((uint32_t)var[1] << 18);
+    uint32_t hi = (uint32_t)var[2] << 4;
+    for (int j = 0; j < 3; ++j) if (neg[j]) hi |= 1u << (24 + j);
+    return (uint64_t)lo | ((uint64_t)hi << 32);
 }
 
 // Arrange the clauses of one level into slots, 8 per quarter-warp (one 128-byte shared-memory
@@ -73,7 +82,7 @@ inline uint64_t pack_entry3(const int32_t* var, const bool* neg) {
 // they cost least.  Returns through `wavefront_sum / wavefront_cnt` the average wavefronts per
 // quarter-warp access.
 inline void pack_level(const odesat_formula& f, const std::vector<int32_t>& clauses, std::vector<int32_t>& out_perm,
-                       std::vector<uint64_t>& out_entry, double& wavefront_sum, int64_t& wavefront_cnt) {
+                       std::vector<uint64_t>& out_entry, double& wavefront_sum, int64_t& wavefront_cnt, bool wide) {
     static const int P[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
     const size_t n = clauses.size();
     // Compact: no holes inside a level (measured on B200: spare hole slots improve the packing
@@ -145,7 +154,7 @@ inline void pack_level(const odesat_formula& f, const std::vector<int32_t>& clau
         for (int k = 0; k < 8; ++k) {
             if (k < b.filled) {
                 out_perm.push_back(b.slot[k].m);
-                out_entry.push_back(pack_entry3(b.slot[k].var, b.slot[k].neg));
+                out_entry.push_back(pack_entry3(b.slot[k].var, b.slot[k].neg, wide));
             } else if (bi != last_used) {   // cannot happen with compact bins; kept as a guard
                 out_perm.push_back(-1);
                 out_entry.push_back(0);
@@ -238,8 +247,9 @@ inline std::shared_ptr<TileLevels> build_tile_levels(const odesat_formula& f, in
 // empty items to a multiple of it (and to more than one ring) so that item i always lives in
 // ring slot i % depth and a slot is stored before it is prefetched again.
 inline std::shared_ptr<TileSchedule> build_tile_schedule(const odesat_formula& f, const TileLevels& lv, int kind, int nt, int depth,
-                                                         bool upload = true) {
+                                                         bool upload = true, bool wide = false) {
     auto s = std::make_shared<TileSchedule>();
+    if (!wide && f.N >= (1 << 14)) throw Error(ODESAT_EUNSUPPORTED, "tile schedule: more than 16383 variables");
     s->kind = kind;
     s->nt = nt;
     s->M = f.M;
@@ -248,7 +258,7 @@ inline std::shared_ptr<TileSchedule> build_tile_schedule(const odesat_formula& f
     for (const auto& b : lv.bucket) {
         if (b.empty()) continue;
         const size_t base0 = s->perm.size();
-        pack_level(f, b, s->perm, s->entry, wsum, wcnt);
+        pack_level(f, b, s->perm, s->entry, wsum, wcnt, wide);
         const size_t n = s->perm.size() - base0;
         while (s->perm.size() % 8) { s->perm.push_back(-1); s->entry.push_back(0); }   // 128-byte aligned level start
         for (size_t o = 0; o < n; o += (size_t)nt) {
