@@ -348,10 +348,12 @@ template <typename T> struct ClusterTileEngine final : TileBase<T> {
         }
         if (pick_cluster(f.N, nt, 8) == 0 && !force_cl) throw Error(ODESAT_EUNSUPPORTED, "variables do not fit in a 4-CTA cluster");
         const int width = cl * nt;
-        // BALANCED levels of about three items (fewer cluster barriers); EXACT levels are what the order allows
-        const int lkey = kind == ODESAT_SCHED_BALANCED ? kind + 16 * (width / 512) : kind;
+        // BALANCED levels of about three items (fewer cluster barriers); EXACT levels are list-scheduled with
+        // the item width as the cap
+        const bool exact = kind == ODESAT_SCHED_EXACT;
+        const int lkey = exact ? 2 * width : 1 + 16 * (width / 512);
         auto lv = f.tile_levels.find(lkey);
-        if (lv == f.tile_levels.end()) lv = f.tile_levels.emplace(lkey, build_tile_levels(f, kind, 3 * width, width)).first;
+        if (lv == f.tile_levels.end()) lv = f.tile_levels.emplace(lkey, build_tile_levels(f, kind, exact ? width : 3 * width, width)).first;
         for (depth = 4; depth >= 2; --depth) {
             const int guess = (int)(f.M / width + 2 * (int64_t)lv->second->bucket.size() + 16);
             if (smem_bytes(f.N, guess, cl, nt, depth) <= kMaxSmem) break;

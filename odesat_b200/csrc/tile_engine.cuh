@@ -682,38 +682,34 @@ template <typename T> struct TileEngine final : TileBase<T> {
 
     TileEngine(const odesat_formula& f_, int64_t R_, int kind, cudaStream_t st, int64_t* ledger) : f(f_), R(R_), stream(st) {
         tiles = (R + W - 1) / W;
-        auto lv = f.tile_levels.find(kind);
-        if (lv == f.tile_levels.end()) lv = f.tile_levels.emplace(kind, build_tile_levels(f, kind)).first;
-        // CTA width: measured on B200 the step time is ≈ items(nt) · (454 + nt) — every item pays a
-        // fixed latency/barrier cost plus an issue cost proportional to the CTA width — so pick the
-        // instantiated width that minimises it for this formula's level sizes.
-        {
-            double best = 1e300;
-            for (int c : {128, 512, 640, 768, 1024}) {
-                double items = 0;
-                for (const auto& b : lv->second->bucket) items += (double)((b.size() + c - 1) / c);
-                const double cost = items * (454.0 + c);
-                if (cost < best) { best = cost; nt = c; }
-            }
-        }
+        // levels: BALANCED colour classes do not depend on the CTA width; EXACT levels are list-scheduled
+        // with the CTA width as the cap (one item per level), so they are built per candidate width
+        auto levels_for = [&](int cap) {
+            const int key = kind == ODESAT_SCHED_EXACT ? kind + 2 * cap : kind;
+            auto it = f.tile_levels.find(key);
+            if (it == f.tile_levels.end())
+                it = f.tile_levels.emplace(key, kind == ODESAT_SCHED_EXACT ? build_tile_levels(f, kind, cap) : build_tile_levels(f, kind)).first;
+            return it->second;
+        };
         static const int cand[] = {128, 512, 640, 768, 1024};
-        if (const char* e = std::getenv("ODESAT_TILE_NT")) {
-            const int v = std::atoi(e);
-            for (int c : cand) if (v == c) nt = v;
-        }
         if (const char* e = std::getenv("ODESAT_TILE_CHUNK")) { const int v = std::atoi(e); if (v > 0) chunk = v; }
+        std::shared_ptr<TileLevels> lv;
         {   // small-instance mode: every level fits in a warp and the whole tile state fits in shared memory
-            size_t maxlev = 0, items32 = 0;
-            for (const auto& b : lv->second->bucket) { maxlev = std::max(maxlev, b.size()); items32 += b.empty() ? 0 : 1; }
             const char* e = std::getenv("ODESAT_TILE_SMALL");
-            small = maxlev <= 32 && smem_small(f.N, (int)items32 + 2) <= kMaxSmem && !(e && e[0] == '0');
+            if (f.M <= 8192 && !(e && e[0] == '0')) {
+                auto l32 = levels_for(32);
+                size_t maxlev = 0, items32 = 0;
+                for (const auto& b : l32->bucket) { maxlev = std::max(maxlev, b.size()); items32 += b.empty() ? 0 : 1; }
+                small = maxlev <= 32 && smem_small(f.N, (int)items32 + 2) <= kMaxSmem;
+                if (small) lv = l32;
+            }
         }
         if (small) {
             nt = 32;
             depth = 1;
             const int key = (kind * 64 + 1) * 16 + 1;
             auto it = f.tile_sched.find(key);
-            if (it == f.tile_sched.end()) it = f.tile_sched.emplace(key, build_tile_schedule(f, *lv->second, kind, 32, 1)).first;
+            if (it == f.tile_sched.end()) it = f.tile_sched.emplace(key, build_tile_schedule(f, *lv, kind, 32, 1)).first;
             sched = it->second;
             chunk = 4096;
             vt.alloc((size_t)(tiles * f.N * W), ledger);
@@ -721,19 +717,35 @@ template <typename T> struct TileEngine final : TileBase<T> {
             oor.alloc(1, ledger);
             return;
         }
+        // CTA width: measured on B200 the step time is ≈ items(nt) · (454 + nt) — every item pays a
+        // fixed latency/barrier cost plus an issue cost proportional to the CTA width — so pick the
+        // instantiated width that minimises it for this formula's level sizes.
+        {
+            int forced = 0;
+            if (const char* e = std::getenv("ODESAT_TILE_NT")) {
+                const int v = std::atoi(e);
+                for (int c : cand) if (v == c) forced = v;
+            }
+            double best = 1e300;
+            for (int c : cand) {
+                if (forced && c != forced) continue;
+                if (pick_depth(f.N, c, (int)(f.M / c + 256)) < 2 && c != 128) continue;   // its ring would not fit
+                auto l = levels_for(c);
+                double items = 0;
+                for (const auto& b : l->bucket) items += (double)((b.size() + c - 1) / c);
+                const double cost = items * (454.0 + c);
+                if (cost < best) { best = cost; nt = c; lv = l; }
+            }
+            if (!lv) { nt = 128; lv = levels_for(128); }
+        }
         int want = 0;
         if (const char* e = std::getenv("ODESAT_TILE_D")) want = std::atoi(e);
-        for (;;) {   // widest CTA first; fall back to a narrower one if its ring does not fit
-            const int guess = (int)(f.M / nt + 3 * (int64_t)lv->second->bucket.size() + 16);
-            depth = pick_depth(f.N, nt, guess);
-            if (depth >= 2 || nt == 128) break;
-            nt = nt == 1024 ? 768 : (nt == 768 ? 640 : (nt == 640 ? 512 : 128));
-        }
+        depth = pick_depth(f.N, nt, (int)(f.M / nt + 3 * (int64_t)lv->bucket.size() + 16));
         if (depth < 2) throw Error(ODESAT_EUNSUPPORTED, "variables do not fit in shared memory");
         if (want >= 2 && want <= depth) depth = want;
         const int key = (kind * 64 + nt / 32) * 16 + depth;
         auto it = f.tile_sched.find(key);
-        if (it == f.tile_sched.end()) it = f.tile_sched.emplace(key, build_tile_schedule(f, *lv->second, kind, nt, depth)).first;
+        if (it == f.tile_sched.end()) it = f.tile_sched.emplace(key, build_tile_schedule(f, *lv, kind, nt, depth)).first;
         sched = it->second;
         if (smem_bytes(f.N, sched->n_items, nt, depth) > kMaxSmem) throw Error(ODESAT_EUNSUPPORTED, "schedule does not fit in shared memory");
         vt.alloc((size_t)(tiles * f.N * W), ledger);
