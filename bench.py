@@ -61,19 +61,62 @@ def algorithmic_bytes_per_step(N, M, Lits, R, P, adaptive=False):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    """Samples the SM clock and the throttle reasons of one GPU WHILE the timed region runs: an NVML
+    polling thread (the timed call is a ctypes call, which releases the GIL), every 2 ms, started
+    before the region so that no sample is lost to start-up.  Falls back to `nvidia-smi -lms`."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index: int, uuid: str | None = None):
+        self.index, self.uuid, self.rows, self.proc, self.t = index, uuid, [], None, None
+        self.stop = threading.Event()
+        self.nvml = None
+
+    def _nvml_loop(self):
+        n, h = self.nvml
+        bits = [(getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8), "hw_slowdown"),
+                (getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40), "hw_thermal_slowdown"),
+                (getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "sw_thermal_slowdown"),
+                (getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4), "sw_power_cap")]
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        while not self.stop.is_set():
+            try:
+                sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+                r = get_reasons(h)
+                self.rows.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for b, _ in bits])
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def __enter__(self):
+        try:
+            import pynvml as n
+            n.nvmlInit()
+            h = None
+            if self.uuid:
+                try:
+                    h = n.nvmlDeviceGetHandleByUUID(self.uuid if self.uuid.startswith("GPU-") else "GPU-" + self.uuid)
+                except Exception:
+                    h = None
+            if h is None:
+                h = n.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml = (n, h)
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+            return self
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "10"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 3.0:      # nvidia-smi is up before the region starts
+                time.sleep(0.01)
+            self.rows.clear()
         except OSError:
             self.proc = None
         return self
@@ -83,8 +126,12 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def __exit__(self, *exc):
+        self.stop.set()
+        if self.nvml is not None:
+            self.t.join(timeout=5)
+            return
         if self.proc:
-            time.sleep(0.06)
+            time.sleep(0.03)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=5)
@@ -94,18 +141,18 @@ class ClockSampler:
 
     def summary(self):
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except (ValueError, IndexError):
                 continue
-            for n, val in zip(names, r[2:6]):
+            for n, val in zip(self.NAMES, r[2:6]):
                 if val.lower().startswith("active"):
                     reasons.add(n)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def measured_peak():
@@ -229,7 +276,11 @@ def run_gpu(args):
     run(args.warmup)
     launches0 = b.launches
     barrier()
-    with ClockSampler(local) as clk:
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        gpu_uuid = None
+    with ClockSampler(local, gpu_uuid) as clk:
         ms = run(args.steps, timed=True)
     barrier()
     n_launch = b.launches - launches0

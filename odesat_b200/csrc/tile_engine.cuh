@@ -232,6 +232,15 @@ template <typename P> __device__ __forceinline__ P* at8(P* base, unsigned idx) {
     asm("mad.wide.u32 %0, %1, 8, %2;" : "=l"(r) : "r"(idx), "l"((unsigned long long)base));
     return (P*)r;
 }
+// Read-only 8-byte load that stays where it is written: a volatile asm is not moved across the other
+// volatile asms (cp.async wait / commit), so the packed clause of the NEXT item is really requested
+// before this item's work — ptxas otherwise sinks the load to the end of the item (ncu: 11.6 % of the
+// stall samples sat on its first use).
+__device__ __forceinline__ uint2 ldg_nc_pinned(const uint2* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -332,7 +341,7 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
                 {   // descriptor (and, without ER, packed clause) of the NEXT item, wrapping into the next step
                     const int i1 = (i + 1 == n_items) ? 0 : i + 1;
                     it_next = s_items[i1];
-                    if (!ER && tid < (it_next.y & 0x7FFFFFFFu)) e_next = __ldg(at8(my_entry, it_next.x));
+                    if (!ER && tid < (it_next.y & 0x7FFFFFFFu)) e_next = ldg_nc_pinned(at8(my_entry, it_next.x));
                 }
                 cp_async_wait<D - 1>();                     // this thread's cell of item i has landed
                 const bool mine = tid < (it.y & 0x7FFFFFFFu);
@@ -685,10 +694,14 @@ template <typename T> struct TileEngine final : TileBase<T> {
         // levels: BALANCED colour classes do not depend on the CTA width; EXACT levels are list-scheduled
         // with the CTA width as the cap (one item per level), so they are built per candidate width
         auto levels_for = [&](int cap) {
-            const int key = kind == ODESAT_SCHED_EXACT ? kind + 2 * cap : kind;
+            const int key = kind + 2 * cap;
             auto it = f.tile_levels.find(key);
-            if (it == f.tile_levels.end())
-                it = f.tile_levels.emplace(key, kind == ODESAT_SCHED_EXACT ? build_tile_levels(f, kind, cap) : build_tile_levels(f, kind)).first;
+            if (it == f.tile_levels.end()) {
+                // BALANCED: colour classes of one item (a CTA width of clauses), capacity rounded to half an item
+                const int target = cap >= 512 ? cap : 1024;
+                it = f.tile_levels.emplace(key, kind == ODESAT_SCHED_EXACT ? build_tile_levels(f, kind, cap)
+                                                                           : build_tile_levels(f, kind, target, target / 2)).first;
+            }
             return it->second;
         };
         static const int cand[] = {128, 512, 640, 768, 1024};
@@ -717,9 +730,11 @@ template <typename T> struct TileEngine final : TileBase<T> {
             oor.alloc(1, ledger);
             return;
         }
-        // CTA width: measured on B200 the step time is ≈ items(nt) · (454 + nt) — every item pays a
-        // fixed latency/barrier cost plus an issue cost proportional to the CTA width — so pick the
-        // instantiated width that minimises it for this formula's level sizes.
+        // CTA width: pick the instantiated width that minimises items(nt) · (454 + nt) for this formula's
+        // level sizes (a fixed per-item cost plus an issue cost proportional to the width).  With levels cut
+        // to the width (list-scheduled EXACT, width-sized BALANCED classes) the measured step time on B200 is
+        // flat within 2 % from 768 to 1024 threads (0.590 / 0.603 / 0.603 ms at 768 / 960 / 1024, BALANCED,
+        // N = 10 000): the kernel is throughput-bound on padded thread slots, not on the item count.
         {
             int forced = 0;
             if (const char* e = std::getenv("ODESAT_TILE_NT")) {
