@@ -7,6 +7,7 @@
 
 #include "formula.hpp"
 #include "kernels_gather.cuh"
+#include "kernels_small.cuh"
 #include "tile_cluster.cuh"
 #include "tile_engine.cuh"
 
@@ -37,6 +38,7 @@ struct BatchBase {
     virtual void run_adaptive(double tol, double zeta, int64_t n, float* ms) = 0;
     virtual void status(int64_t* solved, int64_t* steps) = 0;
     virtual int64_t first_key() = 0;
+    virtual int preferred_chunk() const { return 32; }   // Euler steps between early-exit polls when the caller does not say
     virtual void verify(uint8_t* out) = 0;
     virtual void assignment(int64_t r, uint8_t* out) = 0;
     virtual void get_dt(double* out) = 0;
@@ -315,6 +317,46 @@ template <typename T> struct BatchImpl final : BatchBase {
         else launch_gather_v<MODE, 1>(a);
     }
 
+    // ---- persistent small-instance kernel (kernels_small.cuh) ------------------------------------
+    static constexpr size_t kSmallSmem = 200 * 1024;
+    bool small_ok(bool adaptive) const {
+        const char* e = std::getenv("ODESAT_SMALL");
+        const bool on = !(e && e[0] == '0');
+        return on && !tile && R >= 1 && f->N + f->M > 0 &&
+               small_smem_bytes(f->N, f->M, f->L, adaptive, sizeof(T)) <= kSmallSmem;
+    }
+    int preferred_chunk() const override { return small_ok(true) ? 1024 : 32; }
+    template <int NT> void launch_small_nt(const SmallArgs<T>& a, size_t smem) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            ODESAT_CUDA(cudaFuncSetAttribute(k_solve_small<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmem));
+            attr_set = true;
+        }
+        k_solve_small<T, NT><<<(unsigned)R, NT, smem, stream>>>(a);
+    }
+    void run_small(bool adaptive, double dt, double tol, double zeta, int64_t n, int freeze) {
+        SmallArgs<T> a;
+        a.f = f->dev;
+        a.R = R; a.Rp = Rp;
+        a.v = S[cur].v.p; a.xs = S[cur].xs.p; a.xl = S[cur].xl.p;
+        a.dt_arr = dtv.p;
+        a.solved_step = solved.p;
+        a.dt = (T)dt; a.tol = (T)tol; a.zeta = (T)zeta; a.xl_max = T(1e4) * T(f->M);
+        a.freeze = freeze;
+        a.adaptive = adaptive ? 1 : 0;
+        const size_t smem = small_smem_bytes(f->N, f->M, f->L, adaptive, sizeof(T));
+        for (int64_t done = 0; done < n;) {   // int32 step arguments: at most 2^30 steps per launch
+            const int64_t k = std::min<int64_t>(n - done, int64_t(1) << 30);
+            a.step0 = (int32_t)(step + done);
+            a.nsteps = (int32_t)k;
+            if (f->M > 1024) launch_small_nt<1024>(a, smem);
+            else launch_small_nt<256>(a, smem);
+            ++launches;
+            done += k;
+        }
+        ODESAT_CUDA(cudaGetLastError());
+    }
+
     void time_begin(float* ms) { if (ms) ODESAT_CUDA(cudaEventRecord(ev0, stream)); }
     void time_end(float* ms) {
         if (ms) {
@@ -333,6 +375,13 @@ template <typename T> struct BatchImpl final : BatchBase {
             time_begin(ms);
             if (n > 0) canon_current = false;
             launches += tile->run_fixed((T)dt, (T)zeta, n, freeze, solved.p, step);
+            step += n;
+            time_end(ms);
+            return;
+        }
+        if (small_ok(false)) {
+            time_begin(ms);
+            run_small(false, dt, 0.0, zeta, n, freeze);
             step += n;
             time_end(ms);
             return;
@@ -365,6 +414,13 @@ template <typename T> struct BatchImpl final : BatchBase {
         ODESAT_REQUIRE(n >= 0, "negative step count");
         ODESAT_REQUIRE(step + n < (int64_t(1) << 31) - 4, "step counter overflow");
         if (tile) throw Error(ODESAT_EUNSUPPORTED, "the tile engine integrates fixed steps only; use the gather engine for adaptive steps");
+        if (small_ok(true)) {
+            time_begin(ms);
+            run_small(true, 0.0, tol, zeta, n, 1);
+            step += n;
+            time_end(ms);
+            return;
+        }
         ensure_alt();
         if (!H.allocated()) { H.alloc(f->N, f->M, Rp, &dev_bytes); Fb.alloc(f->N, f->M, Rp, &dev_bytes); }
         time_begin(ms);

@@ -150,9 +150,10 @@ template <typename TH>
 void simulate_impl(const odesat_formula* f, TH* v, TH* xs, TH* xl, const odesat_params* p, uint8_t* assignment,
                    int64_t* steps_taken, int* allsat, double* final_dt) {
     ODESAT_REQUIRE(f && v && xs && xl, "NULL state or formula");
-    const Resolved r = resolve(f, p);
+    Resolved r = resolve(f, p);
     const int eng = (!r.fixed && p->engine == ODESAT_ENGINE_AUTO) ? ODESAT_ENGINE_GATHER : p->engine;
     std::unique_ptr<BatchBase> b(make_batch(f, 1, p->precision, eng, p->schedule));
+    if (p->chunk <= 0) r.chunk = b->preferred_chunk();
     upload_host<TH>(*b, v, xs, xl, true);
     std::vector<int64_t> solved;
     drive(*b, r, ODESAT_MODE_BATCH, solved);
@@ -170,7 +171,7 @@ void simulate_batch_impl(const odesat_formula* f, int64_t R, TH* v, TH* xs, TH* 
                          int64_t* steps_run) {
     ODESAT_REQUIRE(f != nullptr, "formula is NULL");
     ODESAT_REQUIRE(mode == ODESAT_MODE_BATCH || mode == ODESAT_MODE_INTER, "unknown mode");
-    const Resolved r = resolve(f, p);
+    Resolved r = resolve(f, p);
     if (mode == ODESAT_MODE_INTER && !r.fixed)
         throw Error(ODESAT_EUNSUPPORTED, "adaptive `inter` shares one dt across replicas in the reference "
                                          "(system.rs:314); only fixed-step inter is offered");
@@ -178,6 +179,7 @@ void simulate_batch_impl(const odesat_formula* f, int64_t R, TH* v, TH* xs, TH* 
     // the tile engine integrates fixed steps only: adaptive runs resolve AUTO to the gather engine
     const int eng = (!r.fixed && p->engine == ODESAT_ENGINE_AUTO) ? ODESAT_ENGINE_GATHER : p->engine;
     BatchBase* b = cached_batch(f, R, p->precision, eng, p->schedule);
+    if (p->chunk <= 0) r.chunk = b->preferred_chunk();
     const int64_t NONE = std::numeric_limits<int64_t>::max();
     if (!(v && xs && xl)) b->init(seed, replica_offset, true, true, true);       // main.rs:283-289
     if (v || xs || xl) upload_host<TH>(*b, v, xs, xl, (v && xs && xl));

@@ -283,3 +283,40 @@ def test_large_single_instance_adaptive_and_fixed(dtype):
     S.simulate(st, D, None, 0.01, 5, None)
     F.simulate(v, xs, xl, step_size=0.01, steps=5)
     assert eq(st.v, v) and eq(st.xs, xs) and eq(st.xl, xl)
+
+
+@pytest.mark.parametrize("small", ["1", "0"])
+@pytest.mark.parametrize("name", ["aim_sat", "ragged", "rand4"])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_persistent_small_kernel_and_general_engine_agree_with_oracle(golden_dir, monkeypatch, small, name, dtype):
+    """The persistent one-CTA-per-replica kernel (kernels_small.cuh; ODESAT_SMALL=1, default) and the
+    general two-phase engine (ODESAT_SMALL=0) integrate the same trajectories as the oracle, bit for
+    bit: adaptive steps with per-replica dt, fixed steps with and without freezing, ragged clauses."""
+    monkeypatch.setenv("ODESAT_SMALL", small)
+    f = FORMULAS[name](golden_dir)
+    D, F = both(f)
+    prec = L.F64 if dtype == np.float64 else L.F32
+    R = 19
+    zeta = f.default_zeta()
+    # adaptive, 300 steps (some aim-100 replicas flag on the way and must stop untouched)
+    b = B.ReplicaBatch(D, R, prec, L.ENGINE_GATHER)
+    v, xs, xl = F.init_batch(7, R, dtype)
+    b.upload(v, xs, xl)
+    for n in (1, 120, 179):
+        b.run_adaptive(1e-3, zeta, n)
+    ost, odt = F.batch_adaptive(v, xs, xl, 1e-3, zeta, 300)
+    gst, nsteps = b.status()
+    gv, gxs, gxl = b.download()
+    assert nsteps == 300 and eq(gst, ost) and eq(b.dt().astype(dtype), odt)
+    assert eq(gv, v) and eq(gxs, xs) and eq(gxl, xl)
+    # fixed with freezing, continuing from the adaptive state (flags reset by the upload)
+    for freeze in (True, False):
+        b.upload(v, xs, xl)
+        b.run_fixed(0.01, zeta, 150, freeze=freeze)
+        ov, oxs, oxl = v.copy(), xs.copy(), xl.copy()
+        ost = F.batch_fixed(ov, oxs, oxl, 0.01, zeta, 150, freeze=freeze)
+        gst, _ = b.status()
+        gv, gxs, gxl = b.download()
+        assert eq(gst, ost)
+        assert eq(gv, ov) and eq(gxs, oxs) and eq(gxl, oxl)
+    b.close()
