@@ -2,8 +2,9 @@
 // flags (-f -o -t -n -s -l -b, main.rs:31-141) and console lines (main.rs:156-200, 263-320,
 // 335-383).  SURVEY §8f row 1: the DIMACS reader, normaliser and result writer are restated here
 // (cnf.rs:138-219, 246-264, 289-315) so the GPU path is runnable end to end without the Rust crate.
-// Not restated: `-r` ratio preprocessing (cnf.rs:317-840) — `solve` integrates the un-preprocessed
-// formula — and `stoch`.  Extra flags: --seed (the reference's RNG is OS-seeded), --f32.
+// `solve` runs the reference's ratio preprocessing first (`-r`, default 7.0, main.rs:150-166; restated in
+// preprocess.hpp) and replays the elimination trace on the result (main.rs:186-187).  Not restated:
+// `stoch`.  Extra flags: --seed (the reference's RNG is OS-seeded), --f32.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -14,6 +15,7 @@
 #include <set>
 #include <sstream>
 
+#include "preprocess.hpp"
 #include "system.hpp"
 
 using namespace odesat;
@@ -63,13 +65,12 @@ static std::map<std::size_t, std::size_t> normalize(const std::vector<std::vecto
     return name_map;
 }
 
-// cnf.rs:246-264 on the ORIGINAL formula
-static bool evaluate_cnf(const std::map<std::size_t, bool>& values, const std::vector<std::vector<int>>& raw) {
+// cnf.rs:246-264 on the ORIGINAL formula; missing variables are inserted as false (`entry().or_insert(false)`)
+static bool evaluate_cnf(std::map<std::size_t, bool>& values, const std::vector<std::vector<int>>& raw) {
     for (const auto& c : raw) {
         bool sat = false;
         for (int l : c) {
-            auto it = values.find((std::size_t)std::abs(l));
-            const bool val = it != values.end() && it->second;
+            const bool val = values.emplace((std::size_t)std::abs(l), false).first->second;
             sat = sat || (l < 0 ? !val : val);
         }
         if (!sat) return false;
@@ -78,7 +79,7 @@ static bool evaluate_cnf(const std::map<std::size_t, bool>& values, const std::v
 }
 
 static int usage() {
-    std::fprintf(stderr, "usage: odesat_b200_cli <solve|batch|inter> -f FILE [-o OUT] [-t TOL] [-n STEPS] [-s STEP] [-l ZETA] [-b BATCH] [--seed S] [--f32]\n");
+    std::fprintf(stderr, "usage: odesat_b200_cli <solve|batch|inter> -f FILE [-o OUT] [-t TOL] [-n STEPS] [-s STEP] [-l ZETA] [-r RATIO] [-b BATCH] [--seed S] [--f32]\n");
     return 2;
 }
 
@@ -91,6 +92,7 @@ int main(int argc, char** argv) {
     std::size_t batch = 0;
     uint64_t seed = 1;
     bool f32 = false;
+    double ratio = 7.0;                                                     // main.rs:150-154
     for (int i = 2; i < argc; ++i) {
         const std::string a = argv[i];
         auto next = [&]() -> const char* { if (i + 1 >= argc) { usage(); std::exit(2); } return argv[++i]; };
@@ -103,8 +105,32 @@ int main(int argc, char** argv) {
         else if (a == "-b" || a == "--batch-size") batch = (std::size_t)std::atoll(next());
         else if (a == "--seed") seed = (uint64_t)std::atoll(next());
         else if (a == "--f32") f32 = true;
-        else if (a == "-r" || a == "--ctv-ratio") { next(); std::fprintf(stderr, "note: -r preprocessing is out of scope; integrating the formula as given\n"); }
+        else if (a == "-r" || a == "--ctv-ratio") ratio = std::atof(next());
         else return usage();
+    }
+    if (cmd == "preprocess" && !input.empty()) {
+        // host-only helper (no GPU): print the reduced formula of `solve`'s preprocessing in DIMACS form and the
+        // elimination trace, one step per line — used by the CPU tests to compare with odesat_b200/preprocess.py
+        std::ifstream fh(input);
+        if (!fh) { std::perror(input.c_str()); return 1; }
+        std::stringstream ss;
+        ss << fh.rdbuf();
+        std::vector<std::vector<int>> raw;
+        CNFFormula f = parse_dimacs_format(ss.str(), raw);
+        prep::ClauseSet set;
+        for (const auto& c : raw) set.insert(prep::make_clause(c));
+        const prep::Trace trace = prep::repeatedly_resolve_and_update(set, f.varnum, (float)ratio);
+        auto print_clause = [](const prep::Clause& c) {
+            for (prep::Lit l : c) std::printf("%s%zu ", prep::neg_of(l) ? "-" : "", prep::var_of(l));
+            std::printf("0\n");
+        };
+        std::printf("p cnf %zu %zu\n", f.varnum, set.size());
+        for (const auto& c : set) print_clause(c);
+        for (const auto& st : trace) {
+            std::printf("t %s %zu %zu\n", st.ve ? "ve" : "bce", st.var, st.clauses.size());
+            for (const auto& c : st.clauses) { std::printf("t  "); print_clause(c); }
+        }
+        return 0;
     }
     if (input.empty() || (cmd != "solve" && cmd != "batch" && cmd != "inter")) return usage();
     if ((cmd == "batch" || cmd == "inter") && batch == 0) return usage();
@@ -118,8 +144,23 @@ int main(int argc, char** argv) {
         std::printf("Parsing CNF formula...\n");
         std::vector<std::vector<int>> raw;
         CNFFormula f = parse_dimacs_format(ss.str(), raw);
-        std::printf("Normalizing CNF formula...\n");
-        const auto name_map = normalize(raw, f);
+        prep::Trace trace;
+        std::vector<std::vector<int>> integrated = raw;                     // the clauses the ODE is built from
+        if (cmd == "solve") {                                               // main.rs:162-166
+            std::printf("Preprocessing CNF formula...\n");
+            prep::ClauseSet set;
+            for (const auto& c : raw) set.insert(prep::make_clause(c));
+            trace = prep::repeatedly_resolve_and_update(set, f.varnum, (float)ratio);
+            integrated.clear();                                             // convert_to_cnf_formula: BTreeSet order
+            for (const auto& c : set) {
+                std::vector<int> lits;
+                for (prep::Lit l : c) lits.push_back(prep::neg_of(l) ? -(int)prep::var_of(l) : (int)prep::var_of(l));
+                integrated.push_back(lits);
+            }
+        } else {
+            std::printf("Normalizing CNF formula...\n");
+        }
+        const auto name_map = normalize(integrated, f);
         system::Formula F(f);
         std::printf("Simulating...\n");
         odesat_params p = system::make_params(tol, step, steps, zeta);
@@ -135,8 +176,13 @@ int main(int argc, char** argv) {
                                             verified.data(), &winner, assignment.data(), &run));
         std::map<std::size_t, bool> values;                              // cnf.rs:301-315
         for (const auto& kv : name_map) values[kv.first] = assignment[kv.second] != 0;
+        if (cmd == "solve") {
+            std::printf("Mapping values...\n");
+            prep::calculate_trace(values, trace);                           // main.rs:186-187
+            std::printf("Evaluating CNF formula...\n");
+        }
         const bool ok = evaluate_cnf(values, raw);
-        std::printf("\nChecking if solution vector satisfies formula: %s\n", ok ? "true" : "false");
+        std::printf("%sChecking if solution vector satisfies formula: %s\n", cmd == "solve" ? "" : "\n", ok ? "true" : "false");
         std::fprintf(stderr, "[odesat_b200] replicas=%lld steps_run=%lld winner=%lld\n", (long long)R, (long long)run, (long long)winner);
         std::printf("Rendering variable assignments...\n");
         std::string render;                                              // cnf.rs:289-298

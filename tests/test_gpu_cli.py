@@ -40,7 +40,18 @@ def test_batch_on_the_unsat_fixture_is_configs1(golden_dir):
 
 
 def test_solve_adaptive_and_usage_errors(golden_dir):
-    r = run("solve", "-f", str(golden_dir / "aim100_sat.cnf"), "-n", "20000", "--seed", "3")
+    # `solve` = ratio preprocessing (default -r 7, main.rs:150-166) + adaptive integration + trace replay (configs[0])
+    r = run("solve", "-f", str(golden_dir / "aim100_sat.cnf"), "-n", "200000", "--seed", "3")
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    want = ["Reading CNF formula from file...", "Parsing CNF formula...", "Preprocessing CNF formula...", "Clauses: 267 | Vars: 43",
+            "Simulating...", "Mapping values...", "Evaluating CNF formula...", "Checking if solution vector satisfies formula: true",
+            "Rendering variable assignments..."]
+    assert lines[:len(want)] == want
+    values = {int(a): int(b) for a, b in (l.split() for l in lines[len(want) + 1:] if l.strip())}
+    f = cnf.parse_dimacs_format((golden_dir / "aim100_sat.cnf").read_text())
+    assert all(any((values.get(abs(l), 0) == 1) != (l < 0) for l in c) for c in f.clauses)
+    r = run("solve", "-f", str(golden_dir / "aim100_sat.cnf"), "-n", "200000", "-r", "2.5", "--seed", "4", "--f32")
     assert r.returncode == 0 and "satisfies formula: true" in r.stdout
     assert run("batch", "-f", str(golden_dir / "aim100_sat.cnf"), "-b", "4").returncode == 2      # -n is required (main.rs:96)
     assert run("frobnicate").returncode == 2

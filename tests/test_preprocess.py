@@ -90,3 +90,36 @@ def test_ratio_is_reached_or_no_candidate_remains(golden_dir):
     assert np.float32(len(reduced)) / np.float32(max(varnum, 1)) <= np.float32(7.0) + np.float32(1.0)
     # the preprocessed formula has ragged clause lengths — the general engine's job
     assert len({len(c) for c in reduced}) > 1
+
+
+@pytest.mark.parametrize("fixture,ratio", [("aim100_sat.cnf", 7.0), ("aim100_unsat.cnf", 3.0), ("toy_mixed.cnf", 7.0)])
+def test_cpp_host_preprocessing_matches_the_python_restatement(golden_dir, fixture, ratio):
+    """odesat_b200/host/preprocess.hpp (used by the C++ CLI's `solve -r`) and preprocess.py make the same
+    choices (ascending variable order where the reference follows HashSet order): identical reduced
+    formula, identical trace.  `odesat_b200_cli preprocess` is host-only (no GPU)."""
+    import subprocess
+    from pathlib import Path
+    cli = Path(__file__).resolve().parent.parent / "odesat_b200" / "csrc" / "odesat_b200_cli"
+    out = subprocess.run([str(cli), "preprocess", "-f", str(golden_dir / fixture), "-r", str(ratio)],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.splitlines()
+    f = cnf.parse_dimacs_format((golden_dir / fixture).read_text())
+    reduced, varnum, trace = P.repeatedly_resolve_and_update(P.to_clause_set(f.clauses), f.varnum, ratio)
+    assert lines[0] == f"Clauses: {len(reduced)} | Vars: {varnum}"
+    assert lines[1] == f"p cnf {varnum} {len(reduced)}"
+    want = [" ".join(str(l) for l in P.sorted_literals(c)) + " 0" for c in P.sorted_clauses(reduced)]
+    got = [l.strip() for l in lines[2:2 + len(reduced)]]
+    assert got == want
+    tl = lines[2 + len(reduced):]
+    heads = [l.split() for l in tl if not l.startswith("t  ")]
+    assert [(h[1], int(h[2])) for h in heads] == [(s[0], s[1]) for s in trace.steps]
+    # the clauses recorded with each step agree too
+    k = 0
+    for s in trace.steps:
+        assert tl[k].split()[1] == s[0]
+        cl = s[2] if s[0] == "ve" else [s[2]]
+        want_c = [" ".join(str(l) for l in P.sorted_literals(c)) + " 0" for c in P.sorted_clauses(cl)]
+        got_c = [x[3:].strip() for x in tl[k + 1:k + 1 + len(want_c)]]
+        assert got_c == want_c
+        k += 1 + len(want_c)
