@@ -209,18 +209,20 @@ class ShardedResult:
 
 
 def run_sharded_inter(batch, dt: float, zeta: float, max_steps: int, chunk: int, replica_offset: int,
-                      shard_sizes, device=None) -> ShardedResult:
+                      shard_sizes, device=None, reduce_fn=None) -> ShardedResult:
     """`inter` across ranks: every rank steps its shard `chunk` Euler steps at a time, then the
     8-byte MIN all-reduce decides whether anybody flagged.  `batch` needs `.run_fixed(dt, zeta, n,
     freeze)` and `.first_solved()` (ReplicaBatch, or a stub in the CPU tests).  max_steps < 0 runs
-    until some replica flags (system.rs:296-311)."""
+    until some replica flags (system.rs:296-311).  `reduce_fn` replaces the collective (identity for a
+    single-process reference run inside an initialised group)."""
     done = 0
     key = NO_KEY
     while max_steps < 0 or done < max_steps:
         n = chunk if max_steps < 0 else min(chunk, max_steps - done)
         batch.run_fixed(dt, zeta, n, True)
         done += n
-        key = allreduce_min_key(globalize_key(batch.first_solved(), replica_offset), device)
+        local_key = globalize_key(batch.first_solved(), replica_offset)
+        key = reduce_fn(local_key) if reduce_fn is not None else allreduce_min_key(local_key, device)
         if key != NO_KEY:
             break
     winner, wrank = -1, -1

@@ -263,6 +263,7 @@ template <typename T> struct BatchImpl final : BatchBase {
         a.rep1 = R;
         a.cstride = (slabbed && slab > 0) ? slab : Rp;
         a.zeta = (T)zeta;
+        if (const char* e = std::getenv("ODESAT_GATHER_L2HINTS")) a.l2_hints = std::atoi(e);
         a.xl_max = T(1e4) * T(f->M);
         a.solved_step = solved.p;
         a.unsat = unsat.p;
@@ -276,10 +277,10 @@ template <typename T> struct BatchImpl final : BatchBase {
     // one RHS evaluation + update = clause phase, then variable phase; 16 bytes of replicas per
     // thread when the rows are 16-byte aligned (R >= 32 ⇒ Rp is a multiple of 32)
     static constexpr int VW = 16 / (int)sizeof(T);
-    template <int V> void geom_v(int64_t rows, int64_t reps, int rows_per_thread, dim3& grid, dim3& block) const {
+    template <int V> void geom_v(int64_t rows, int64_t reps, int rows_per_thread, dim3& grid, dim3& block, int bx_cap = 256) const {
         const int64_t rv = (reps + V - 1) / V;
         int bx = 1;
-        while (bx < 256 && bx < rv) bx <<= 1;
+        while (bx < bx_cap && bx < rv) bx <<= 1;
         const int by = 256 / bx;
         block = dim3(bx, by, 1);
         const int64_t rpb = (int64_t)by * rows_per_thread;
@@ -298,7 +299,9 @@ template <typename T> struct BatchImpl final : BatchBase {
                 // streaming clause phase: RPT rows per thread, all their loads in flight as cp.async copies
                 constexpr int CB = VC * (int)sizeof(T);
                 constexpr int RPT = CB == 16 ? 2 : 4;
-                geom_v<VC>(f->M, reps, RPT, g, b);
+                int cap = 256;
+                if (const char* e = std::getenv("ODESAT_GATHER_BX")) { const int v = std::atoi(e); if (v >= 1 && v <= 256) cap = v; }
+                geom_v<VC>(f->M, reps, RPT, g, b, cap);
                 k_clause_stream<T, MODE, VC, RPT><<<g, b, (size_t)RPT * 5 * 256 * CB, stream>>>(a);
             } else {
                 geom_v<VC>(f->M, reps, a.rows_per_thread, g, b);

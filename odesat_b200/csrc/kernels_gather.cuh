@@ -29,6 +29,7 @@ template <typename T> struct GatherArgs {
     int64_t rep0 = 0, rep1 = 0;   // replicas [rep0, rep1) of this launch (a SLAB; the whole batch when not slabbed)
     int64_t cstride = 0;          // row stride of contrib (Rp, or the slab width: contrib[slot][rep - rep0])
     int rows_per_thread = 8;      // rows a thread walks per launch: fewer, fatter blocks
+    int l2_hints = 0;             // evict-first on the once-per-step streams, evict-last on the v gathers
     const T *v = nullptr, *xs = nullptr, *xl = nullptr;   // state the RHS is evaluated on
     T *ov = nullptr, *oxs = nullptr, *oxl = nullptr;      // FIXED: y(t+1) (may alias the inputs); DERIV: dy; A: y_half; B: y_new
     T *fv = nullptr, *fxs = nullptr, *fxl = nullptr;      // A: y_full (out); B: y_full (in)
@@ -82,6 +83,25 @@ template <typename T, int V> __device__ __forceinline__ void vstore(T* p, const 
     }
 }
 
+
+// streaming (evict-first) variants for data that is touched once per step: keeps the L2 for the v rows,
+// which every clause of a variable re-reads
+template <typename T, int V> __device__ __forceinline__ void vstore_cs(T* p, const RVec<T, V>& r) {
+    if (V * sizeof(T) == 16) __stcs(reinterpret_cast<int4*>(p), *reinterpret_cast<const int4*>(r.x));
+    else {
+#pragma unroll
+        for (int u = 0; u < V; ++u) __stcs(p + u, r.x[u]);
+    }
+}
+template <typename T, int V> __device__ __forceinline__ RVec<T, V> vload_cs(const T* p) {
+    RVec<T, V> r;
+    if (V * sizeof(T) == 16) *reinterpret_cast<int4*>(r.x) = __ldcs(reinterpret_cast<const int4*>(p));
+    else {
+#pragma unroll
+        for (int u = 0; u < V; ++u) r.x[u] = __ldcs(p + u);
+    }
+    return r;
+}
 
 // ---- clause phase: system.rs:41-88 for one clause and V replicas ----------------------------
 template <typename T, int K, int MODE, int V>
@@ -233,6 +253,22 @@ template <int BYTES> __device__ __forceinline__ void cp_async_n(void* smem, cons
     else if (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
     else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
 }
+template <int BYTES> __device__ __forceinline__ void cp_async_n_hint(void* smem, const void* gmem, unsigned long long pol) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    if (BYTES == 16) asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "l"(pol) : "memory");
+    else if (BYTES == 8) asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(s), "l"(gmem), "l"(pol) : "memory");
+    else asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"(s), "l"(gmem), "l"(pol) : "memory");
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ void cp_async_commit_g() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_dyn(int n) {   // wait until at most n groups are pending
     switch (n) {
@@ -270,6 +306,7 @@ __global__ void __launch_bounds__(256) k_clause_stream(const GatherArgs<T> a) {
         all_skip = all_skip && sk;
         dt[u] = (a.dt_arr && rep_ok) ? a.dt_arr[rep + u < a.R ? rep + u : rep] : a.dt;
     }
+    const unsigned long long pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
     int lit[RPT][3];
     int64_t mrow[RPT];
     bool ok[RPT];
@@ -289,10 +326,16 @@ __global__ void __launch_bounds__(256) k_clause_stream(const GatherArgs<T> a) {
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
                 const int var = (lit[r][j] < 0 ? -lit[r][j] : lit[r][j]) - 1;
-                cp_async_n<CB>(cell(r, j), a.v + (int64_t)var * Rp + rep);
+                if (a.l2_hints) cp_async_n_hint<CB>(cell(r, j), a.v + (int64_t)var * Rp + rep, pol_keep);
+                else cp_async_n<CB>(cell(r, j), a.v + (int64_t)var * Rp + rep);
             }
-            cp_async_n<CB>(cell(r, 3), a.xs + at);
-            cp_async_n<CB>(cell(r, 4), a.xl + at);
+            if (a.l2_hints) {
+                cp_async_n_hint<CB>(cell(r, 3), a.xs + at, pol_stream);
+                cp_async_n_hint<CB>(cell(r, 4), a.xl + at, pol_stream);
+            } else {
+                cp_async_n<CB>(cell(r, 3), a.xs + at);
+                cp_async_n<CB>(cell(r, 4), a.xl + at);
+            }
         }
         cp_async_commit_g();
     }
@@ -346,7 +389,8 @@ __global__ void __launch_bounds__(256) k_clause_stream(const GatherArgs<T> a) {
                 const T rr = (c[u] == val) ? T(0.5) * (qs[j] - vis[j].x[u]) : T(0);    // :73-77
                 t.x[u] = w[u] * g + rg[u] * rr;                                        // the addend of :80
             }
-            vstore<T, V>(a.contrib + (mrow[r] * 3 + j) * a.cstride + (rep - a.rep0), t);
+            if (a.l2_hints) vstore_cs<T, V>(a.contrib + (mrow[r] * 3 + j) * a.cstride + (rep - a.rep0), t);
+            else vstore<T, V>(a.contrib + (mrow[r] * 3 + j) * a.cstride + (rep - a.rep0), t);
         }
         const T hi_s = T(1) - Kc<T>::EPSILON;
         RVec<T, V> o1, o2, f1, f2;
@@ -388,8 +432,8 @@ __global__ void __launch_bounds__(256) k_clause_stream(const GatherArgs<T> a) {
                 else if (rep + u < a.R) err_max<T>(a.err + rep + u, rmax(fabs(fx.x[u] - o1.x[u]), fabs(fl.x[u] - o2.x[u])));   // :104-107
             }
         }
-        vstore<T, V>(a.oxs + at, o1);
-        vstore<T, V>(a.oxl + at, o2);
+        if (a.l2_hints) { vstore_cs<T, V>(a.oxs + at, o1); vstore_cs<T, V>(a.oxl + at, o2); }
+        else { vstore<T, V>(a.oxs + at, o1); vstore<T, V>(a.oxl + at, o2); }
     }
 }
 
@@ -434,7 +478,10 @@ __device__ __forceinline__ void var_row(const GatherArgs<T>& a, int64_t row, int
         RVec<T, V> t[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if (e + k < e1) t[k] = vload_rw<T, V>(a.contrib + (int64_t)__ldg(a.f.occ_slot + e + k) * a.cstride + (rep - a.rep0));
+            if (e + k < e1) {
+                const T* cp = a.contrib + (int64_t)__ldg(a.f.occ_slot + e + k) * a.cstride + (rep - a.rep0);
+                t[k] = a.l2_hints ? vload_cs<T, V>(cp) : vload_rw<T, V>(cp);
+            }
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             if (e + k < e1) {
