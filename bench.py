@@ -88,7 +88,7 @@ class ClockSampler:
                 self.rows.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for b, _ in bits])
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.001)
 
     def __enter__(self):
         try:
@@ -105,6 +105,10 @@ class ClockSampler:
             self.nvml = (n, h)
             self.t = threading.Thread(target=self._nvml_loop, daemon=True)
             self.t.start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 2.0:      # NVML is warm before the region starts
+                time.sleep(0.001)
+            self.rows.clear()
             return self
         except Exception:
             self.nvml = None

@@ -31,7 +31,8 @@ struct BatchBase {
         if (stream) cudaStreamDestroy(stream);
     }
     virtual void reset() = 0;   // flags, step counter, dt back to the state of a fresh batch
-    virtual void init(uint64_t seed, int64_t replica_offset, bool gen_v, bool gen_xs, bool gen_xl) = 0;
+    // finalize = false: an upload() of the remaining arrays follows immediately (saves one layout conversion)
+    virtual void init(uint64_t seed, int64_t replica_offset, bool gen_v, bool gen_xs, bool gen_xl, bool finalize = true) = 0;
     virtual void upload(const void* v, const void* xs, const void* xl, bool reset) = 0;
     virtual void download(void* v, void* xs, void* xl) = 0;
     virtual void run_fixed(double dt, double zeta, int64_t n, int freeze, float* ms) = 0;
@@ -182,8 +183,9 @@ template <typename T> struct BatchImpl final : BatchBase {
         return S[cur];
     }
     bool canon_current = false;   // S[0] mirrors the tile engine's state (skip redundant exports)
+    bool canon_ahead = false;     // S[0] holds NEWER data than the tile layout (init without finalize): import before stepping
     void tile_to_canon() {
-        if (tile && !canon_current) {
+        if (tile && !canon_current && !canon_ahead) {
             canon();
             launches += tile->export_state(S[0].v.p, S[0].xs.p, S[0].xl.p, Rp);
             canon_current = true;
@@ -193,12 +195,15 @@ template <typename T> struct BatchImpl final : BatchBase {
         if (tile) {
             launches += tile->import_state(S[0].v.p, S[0].xs.p, S[0].xl.p, Rp);
             canon_current = true;
+            canon_ahead = false;
         }
     }
 
-    void init(uint64_t seed, int64_t replica_offset, bool gen_v, bool gen_xs, bool gen_xl) override {
+    void init(uint64_t seed, int64_t replica_offset, bool gen_v, bool gen_xs, bool gen_xl, bool finalize = true) override {
         StateBuf<T>& s = canon();
-        if (tile && !(gen_v && gen_xs && gen_xl)) tile_to_canon();
+        if (tile && !(gen_v && gen_xs && gen_xl) && !finalize) {
+            // the caller uploads the arrays that are not generated here: nothing of the old state survives
+        } else if (tile && !(gen_v && gen_xs && gen_xl)) tile_to_canon();
         dim3 g, b;
         geom(f->N + f->M, g, b);
         if (f->N + f->M > 0 && R > 0) {
@@ -207,6 +212,7 @@ template <typename T> struct BatchImpl final : BatchBase {
             ++launches;
         }
         ODESAT_CUDA(cudaGetLastError());
+        if (tile && !finalize) { canon_ahead = true; canon_current = false; return; }
         canon_to_tile();
         ODESAT_CUDA(cudaStreamSynchronize(stream));
     }
@@ -375,6 +381,7 @@ template <typename T> struct BatchImpl final : BatchBase {
         ODESAT_REQUIRE(n >= 0, "negative step count");
         ODESAT_REQUIRE(step + n < (int64_t(1) << 31) - 4, "step counter overflow");
         if (tile) {
+            if (canon_ahead) canon_to_tile();
             time_begin(ms);
             if (n > 0) canon_current = false;
             launches += tile->run_fixed((T)dt, (T)zeta, n, freeze, solved.p, step);

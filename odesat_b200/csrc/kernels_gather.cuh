@@ -622,7 +622,7 @@ __global__ void k_verify(const FormulaDev f, const T* v, int64_t R, int64_t Rp, 
         const bool val = v[(int64_t)var * Rp + rep] > T(0);
         sat = sat || (lit < 0 ? !val : val);
     }
-    if (!sat) bad[rep] = 1u;
+    if (!sat && bad[rep] == 0u) bad[rep] = 1u;   // raised only: test first, every falsified clause of a replica hits the same word
 }
 
 template <typename T>

@@ -181,7 +181,8 @@ void simulate_batch_impl(const odesat_formula* f, int64_t R, TH* v, TH* xs, TH* 
     BatchBase* b = cached_batch(f, R, p->precision, eng, p->schedule);
     if (p->chunk <= 0) r.chunk = b->preferred_chunk();
     const int64_t NONE = std::numeric_limits<int64_t>::max();
-    if (!(v && xs && xl)) b->init(seed, replica_offset, true, true, true);       // main.rs:283-289
+    // main.rs:283-289: whatever the caller does not supply is generated on the device
+    if (!(v && xs && xl)) b->init(seed, replica_offset, !v, !xs, !xl, /*finalize=*/!(v || xs || xl));
     if (v || xs || xl) upload_host<TH>(*b, v, xs, xl, (v && xs && xl));
     std::vector<int64_t> solved;
     const int64_t key = drive(*b, r, mode, solved);
