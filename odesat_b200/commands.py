@@ -9,6 +9,7 @@ Everything numeric runs through libodesat_b200 on the GPU; there is no CPU fallb
 """
 from __future__ import annotations
 
+import time
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional
 
@@ -29,6 +30,8 @@ class CommandResult:
     winner: int = -1
     n_vars: int = 0                    # size of the integrated (preprocessed, normalised) formula
     n_clauses: int = 0
+    seconds_preprocess: float = 0.0    # host-side ratio preprocessing (solve only)
+    seconds_integrate: float = 0.0     # formula upload + GPU integration
 
 
 def evaluate_cnf(values: Dict[int, bool], clauses: List[List[int]]) -> bool:
@@ -74,12 +77,15 @@ def solve(input: str, output: Optional[str] = None, tolerance: Optional[float] =
     ratio = 7.0 if ctv_ratio is None else ctv_ratio                              # main.rs:150-154
     original = _read(input, log)
     log("Preprocessing CNF formula...")
+    t0 = time.perf_counter()
     clauses, varnum, trace = preprocess.repeatedly_resolve_and_update(
         preprocess.to_clause_set(original.clauses), original.varnum, ratio, log=log)
+    t_pre = time.perf_counter() - t0
     # convert_to_cnf_formula (cnf.rs:397-416): clause and literal order = BTreeSet order
     reduced = cnf.CNF([preprocess.sorted_literals(c) for c in preprocess.sorted_clauses(clauses)], varnum)
     formula = cnf.normalize_cnf_variables(reduced)
     log("Simulating...")
+    t0 = time.perf_counter()
     F = DeviceFormula(formula)
     dtype = np.float32 if precision == L.F32 else np.float64
     rng = np.random.default_rng(seed)
@@ -88,11 +94,13 @@ def solve(input: str, output: Optional[str] = None, tolerance: Optional[float] =
     info: list = []
     result = simulate(state, F, tolerance, step_size, step_number, learning_rate, info=info)
     F.close()
+    t_int = time.perf_counter() - t0
     log("Mapping values...")
     values = formula.map_values_by_indices(result)
     preprocess.calculate_trace(values, trace)                                    # main.rs:186-187
     log("Evaluating CNF formula...")
-    res = CommandResult(False, {}, "", steps=info[0].steps_taken, n_vars=formula.varnum, n_clauses=formula.n_clauses)
+    res = CommandResult(False, {}, "", steps=info[0].steps_taken, n_vars=formula.varnum, n_clauses=formula.n_clauses,
+                        seconds_preprocess=t_pre, seconds_integrate=t_int)
     return _finish(values, original, output, log, res)
 
 
