@@ -43,16 +43,25 @@ typedef enum odesat_status {
 typedef enum odesat_precision { ODESAT_F64 = 0, ODESAT_F32 = 1 } odesat_precision;
 
 /* Which kernel family integrates a replica batch.
- *  GATHER: general path — any clause length, any N/M/R; replica-major state [row][replica];
- *          per-variable gather over the variable→clause transpose, contributions added in the
- *          reference's order (ascending clause, then literal position) ⇒ bit-identical sums.
- *  TILE  : throughput path — uniform clause length k<=3.., variables of a replica
- *          tile resident in shared memory, clauses streamed in conflict-free levels. */
+ *  GATHER: general path — any clause length, any N/M/R, fixed and adaptive steps; replica-major
+ *          state [row][replica]; a clause phase materialises the per-literal contributions, a
+ *          variable phase adds them over the variable→clause transpose in the reference's order
+ *          (ascending clause, then literal position) ⇒ bit-identical sums.  Instances whose whole
+ *          state fits in the shared memory of one SM (the reference's fixtures) run on a persistent
+ *          one-CTA-per-replica kernel with the step loop inside the kernel.
+ *  TILE  : throughput path — fixed steps, uniform 3-literal clauses with distinct variables, up to
+ *          ≈ 13 000 variables (two f32 replicas / one f64 replica per CTA) or ≈ 27 000 (one f32
+ *          replica per CTA): variables of a replica tile resident in shared memory, clauses
+ *          streamed in conflict-free levels.  Larger instances can be forced onto a thread-block
+ *          cluster (rows in distributed shared memory) by requesting TILE explicitly; AUTO does
+ *          not, because the general engine is faster there.
+ *  AUTO  : TILE when it applies and the batch has at least 8 replicas, else GATHER. */
 typedef enum odesat_engine { ODESAT_ENGINE_AUTO = 0, ODESAT_ENGINE_GATHER = 1, ODESAT_ENGINE_TILE = 2 } odesat_engine;
 
 /* Clause schedule of the TILE engine.
- *  EXACT   : order-preserving levelisation — each variable receives its clause contributions in
- *            ascending clause index, i.e. the reference's summation order (bit-identical dv).
+ *  EXACT   : order-preserving levels (list scheduling) — each variable receives its clause
+ *            contributions in ascending clause index, i.e. the reference's summation order
+ *            (bit-identical dv).
  *  BALANCED: equal-size colour classes (fewer barriers); per-variable summation order differs
  *            from the reference's, results agree to rounding (deterministic run to run). */
 typedef enum odesat_schedule { ODESAT_SCHED_EXACT = 0, ODESAT_SCHED_BALANCED = 1 } odesat_schedule;
@@ -73,7 +82,8 @@ typedef struct odesat_params {
     int32_t precision;   /* odesat_precision of the device arithmetic                           */
     int32_t engine;      /* odesat_engine                                                       */
     int32_t schedule;    /* odesat_schedule                                                     */
-    int32_t chunk;       /* Euler steps between early-exit polls; <= 0 → 32                     */
+    int32_t chunk;       /* Euler steps between early-exit polls; <= 0 → 32 (1024 on the persistent
+                            small-instance kernel)                                               */
 } odesat_params;
 
 typedef struct odesat_formula odesat_formula;   /* device-resident CSR + variable→clause transpose */
