@@ -92,3 +92,36 @@ def test_aim_fixture_schedule(golden_dir):
     f = cnf.load_dimacs(str(golden_dir / "aim100_sat.cnf"))
     nlev, items, perm, wf = compile_schedule(f, L.SCHED_EXACT, 128, 6)
     assert nlev >= 8 and sorted(perm[perm >= 0]) == list(range(160))
+
+
+@pytest.mark.parametrize("threads", [128, 512, 1024])
+def test_exact_levels_are_list_scheduled_to_the_cta_width(threads):
+    """EXACT levels are capped at the CTA width (one item per level) without lengthening the schedule
+    beyond the critical path of the per-variable clause chains, and stay order-preserving."""
+    f = cnf.random_ksat(4000, 4.3, seed=11)
+    nlev, items, perm, _ = compile_schedule(f, L.SCHED_EXACT, threads, 2)
+    levels = levels_of(items, perm)
+    assert max(len(lv) for lv in levels) <= threads
+    assert sum(1 for it in items if ((int(it) >> 20) & 0x7FF) > 0) == len(levels)      # one item per level
+    # critical path: longest chain of clauses linked through a shared variable, in clause order
+    var = (np.abs(f.lits) - 1).reshape(-1, 3)
+    depth = np.zeros(f.n_clauses, int)
+    last = {}
+    for m in range(f.n_clauses):
+        d = 0
+        for v in var[m]:
+            if v in last:
+                d = max(d, depth[last[v]] + 1)
+            last[v] = m
+        depth[m] = d
+    critical = int(depth.max()) + 1
+    assert nlev >= critical
+    if threads >= 512:
+        assert nlev == critical                      # enough lanes: the cap costs no extra level
+    # order preservation: every variable meets its clauses in ascending clause index, one level apart at least
+    level_of = {m: k for k, lv in enumerate(levels) for m in lv}
+    last_level = {}
+    for m in range(f.n_clauses):
+        for v in var[m]:
+            assert last_level.get(v, -1) < level_of[m]
+            last_level[v] = level_of[m]
