@@ -175,7 +175,11 @@ int odesat_simulate_f32(const odesat_formula* f, float* v, float* xs, float* xl,
  *                 system.rs:357)
  *  assignment   : [N] thresholded state of the winner
  *  steps_run    : outer Euler steps executed by the device loop
- * Adaptive INTER (shared dt across replicas) is not offered: ODESAT_EUNSUPPORTED. */
+ * Adaptive INTER (params.step_size = NaN) runs the reference's loop literally: the replicas take their steps
+ * one after the other inside an outer step and share ONE dt (system.rs:314), and the loop
+ * stops right after the outer step in which the first replica flags — a sequential dependency replica →
+ * replica, so it is correct but not fast (one CTA walks the replicas on instances that fit in shared memory;
+ * otherwise the general engine steps one replica at a time). */
 int odesat_simulate_batch(const odesat_formula* f, int64_t R, double* v, double* xs, double* xl,
                           uint64_t seed, int64_t replica_offset, const odesat_params* params,
                           int32_t mode, int32_t write_back, int64_t* solved_step,

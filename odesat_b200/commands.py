@@ -127,9 +127,9 @@ def inter(input: str, batch_size: int, output: Optional[str] = None, tolerance: 
           step_number: Optional[int] = None, step_size: Optional[float] = None,
           learning_rate: Optional[float] = None, *, seed: int = 0, precision: int = L.F64,
           log: Callable[[str], None] = print) -> CommandResult:
-    """main.rs:326-386: B replicas in lock-step, stop at the first flag (system.rs:241-359).  Fixed step
-    only: without -s the reference shares one adaptive dt across replicas (quirk Q7), which the
-    library refuses (ODESAT_EUNSUPPORTED) rather than approximates."""
+    """main.rs:326-386: B replicas in lock-step, stop at the first flag (system.rs:241-359).  Without -s
+    the reference shares one adaptive dt across the replicas (quirk Q7); the library runs that loop
+    literally (sequential over replicas)."""
     original = _read(input, log)
     log("Normalizing CNF formula...")
     formula = cnf.normalize_cnf_variables(original)

@@ -37,6 +37,9 @@ struct BatchBase {
     virtual void download(void* v, void* xs, void* xl) = 0;
     virtual void run_fixed(double dt, double zeta, int64_t n, int freeze, float* ms) = 0;
     virtual void run_adaptive(double tol, double zeta, int64_t n, float* ms) = 0;
+    // adaptive `simulate_inter` with the reference's shared dt (system.rs:312-349): sequential over replicas;
+    // runs until some replica flags or max_steps (< 0: unbounded) outer steps are done; returns the outer steps run
+    virtual int64_t run_inter_adaptive(double tol, double zeta, int64_t max_steps) = 0;
     virtual void status(int64_t* solved, int64_t* steps) = 0;
     virtual int64_t first_key() = 0;
     virtual int preferred_chunk() const { return 32; }   // Euler steps between early-exit polls when the caller does not say
@@ -457,6 +460,83 @@ template <typename T> struct BatchImpl final : BatchBase {
             ++step;
         }
         time_end(ms);
+    }
+
+    int64_t run_inter_adaptive(double tol, double zeta, int64_t max_steps) override {
+        if (tile) throw Error(ODESAT_EUNSUPPORTED, "adaptive inter runs on the gather engine");
+        if (R == 0) return 0;
+        const int64_t NONE = std::numeric_limits<int64_t>::max();
+        DevBuf<int32_t> d_done;
+        d_done.alloc(1);
+        int64_t done = 0;
+        // dtv[0] is the shared dt on the small path; the general path keeps it in a separate slot
+        if (small_ok(true)) {
+            SmallArgs<T> a;
+            a.f = f->dev;
+            a.R = R; a.Rp = Rp;
+            a.v = S[cur].v.p; a.xs = S[cur].xs.p; a.xl = S[cur].xl.p;
+            a.dt_arr = dtv.p;
+            a.solved_step = solved.p;
+            a.tol = (T)tol; a.zeta = (T)zeta; a.xl_max = T(1e4) * T(f->M);
+            a.adaptive = 1;
+            const size_t smem = small_smem_bytes(f->N, f->M, f->L, true, sizeof(T));
+            while (max_steps < 0 || done < max_steps) {
+                const int64_t k = max_steps < 0 ? (int64_t(1) << 16) : std::min<int64_t>(max_steps - done, int64_t(1) << 16);
+                a.step0 = (int32_t)(step + done);
+                a.nsteps = (int32_t)k;
+                if (f->M > 1024) {
+                    ODESAT_CUDA(cudaFuncSetAttribute(k_inter_adaptive_small<T, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmem));
+                    k_inter_adaptive_small<T, 1024><<<1, 1024, smem, stream>>>(a, d_done.p);
+                } else {
+                    ODESAT_CUDA(cudaFuncSetAttribute(k_inter_adaptive_small<T, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmem));
+                    k_inter_adaptive_small<T, 256><<<1, 256, smem, stream>>>(a, d_done.p);
+                }
+                ++launches;
+                int32_t h = 0;
+                ODESAT_CUDA(cudaMemcpyAsync(&h, d_done.p, 4, cudaMemcpyDeviceToHost, stream));
+                ODESAT_CUDA(cudaStreamSynchronize(stream));
+                ODESAT_CUDA(cudaGetLastError());
+                done += h;
+                if (first_key() != NONE) break;
+            }
+            step += done;
+            return done;
+        }
+        // general engine: the five launches of an adaptive step on ONE replica at a time; the shared dt
+        // travels through dt_shared ↔ dtv[r] around each replica's step
+        ensure_alt();
+        if (!H.allocated()) { H.alloc(f->N, f->M, Rp, &dev_bytes); Fb.alloc(f->N, f->M, Rp, &dev_bytes); }
+        DevBuf<T> dt_shared;
+        dt_shared.alloc(1);
+        ODESAT_CUDA(cudaMemcpyAsync(dt_shared.p, dtv.p, sizeof(T), cudaMemcpyDeviceToDevice, stream));
+        while (max_steps < 0 || done < max_steps) {
+            for (int64_t r = 0; r < R; ++r) {
+                ODESAT_CUDA(cudaMemcpyAsync(dtv.p + r, dt_shared.p, sizeof(T), cudaMemcpyDeviceToDevice, stream));
+                GatherArgs<T> a = base_args(zeta);
+                a.rep0 = r; a.rep1 = r + 1;
+                a.dt_arr = dtv.p;
+                a.step = (int32_t)(step + done);
+                a.v = S[cur].v.p; a.xs = S[cur].xs.p; a.xl = S[cur].xl.p;
+                a.ov = H.v.p; a.oxs = H.xs.p; a.oxl = H.xl.p;
+                a.fv = Fb.v.p; a.fxs = Fb.xs.p; a.fxl = Fb.xl.p;
+                a.yv = S[cur].v.p; a.yxs = S[cur].xs.p; a.yxl = S[cur].xl.p;
+                launch_gather_v<G_ADAPT_A, 1>(a);
+                a.v = H.v.p; a.xs = H.xs.p; a.xl = H.xl.p;
+                a.ov = S[1 - cur].v.p; a.oxs = S[1 - cur].xs.p; a.oxl = S[1 - cur].xl.p;
+                launch_gather_v<G_ADAPT_B, 1>(a);
+                k_adapt_c<T><<<1, 32, 0, stream>>>(solved.p + r, unsat.p + r, err.p + r, dtv.p + r, (T)tol, 1, (int32_t)(step + done));
+                ++launches;
+                ODESAT_CUDA(cudaMemcpyAsync(dt_shared.p, dtv.p + r, sizeof(T), cudaMemcpyDeviceToDevice, stream));
+            }
+            cur = 1 - cur;
+            ++done;
+            if (first_key() != NONE) break;
+        }
+        ODESAT_CUDA(cudaMemcpyAsync(dtv.p, dt_shared.p, sizeof(T), cudaMemcpyDeviceToDevice, stream));
+        ODESAT_CUDA(cudaStreamSynchronize(stream));
+        ODESAT_CUDA(cudaGetLastError());
+        step += done;
+        return done;
     }
 
     void status(int64_t* out, int64_t* steps) override {

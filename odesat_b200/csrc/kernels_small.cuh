@@ -69,107 +69,167 @@ template <typename T> __device__ __forceinline__ T small_dv(const FormulaDev& f,
     return dv;
 }
 
+// Shared-memory arrays of one resident replica.
+template <typename T> struct SmallSmem {
+    T *yv, *yxs, *yxl, *contrib, *hv, *hxs, *hxl, *fv, *fxs, *fxl;
+    typename ErrBits<T>::U* red;
+    __device__ SmallSmem(unsigned char* base, int N, int M, int L, bool adaptive) {
+        yv = reinterpret_cast<T*>(base);
+        yxs = yv + N;
+        yxl = yxs + M;
+        contrib = yxl + M;
+        hv = contrib + L;          // adaptive only: y_half, y_full
+        hxs = hv + N;
+        hxl = hxs + M;
+        fv = hxl + M;
+        fxs = fv + N;
+        fxl = fxs + M;
+        red = reinterpret_cast<typename ErrBits<T>::U*>(
+            base + (((adaptive ? 3 : 1) * (size_t)(N + 2 * M) + (size_t)L) * sizeof(T) + 15) / 16 * 16);
+    }
+};
+
+// One step of the resident replica (all threads of the CTA; ends with the state complete and a
+// block barrier passed).  Returns the all-clauses-satisfied flag of the PRE-update state (uniform).
+//   fixed    (system.rs:141-154): the update always happens.
+//   adaptive (system.rs:111-139): flagged ⇒ state and dt untouched; else one full step vs two half
+//            steps, dt ← clamp(dt·sqrt(tol / err), 2^-7, 1e3).
+template <typename T, int NT>
+__device__ __forceinline__ bool small_step(const FormulaDev& f, const SmallSmem<T>& sm, bool adaptive, T& dt, T tol, T zeta, T xl_max) {
+    using U = typename ErrBits<T>::U;
+    const int N = (int)f.N, M = (int)f.M;
+    const int tid = threadIdx.x;
+    const T hi_s = T(1) - Kc<T>::EPSILON;
+    // ---- k1 = f(y) ------------------------------------------------------------------------
+    bool unsat = false;
+    const T h = T(0.5) * dt;
+    for (int m = tid; m < M; m += NT) {
+        T dxs, dxl;
+        const T x = sm.yxs[m], l = sm.yxl[m];
+        unsat = !small_clause<T>(f, m, sm.yv, x, l, zeta, sm.contrib, dxs, dxl) || unsat;
+        if (adaptive) {
+            sm.hxs[m] = euler_clamp(x, dxs, h, Kc<T>::EPSILON, hi_s);      // :128
+            sm.hxl[m] = euler_clamp(l, dxl, h, T(1), xl_max);
+            sm.fxs[m] = euler_clamp(x, dxs, dt, Kc<T>::EPSILON, hi_s);     // :125
+            sm.fxl[m] = euler_clamp(l, dxl, dt, T(1), xl_max);
+        } else {
+            sm.yxs[m] = euler_clamp(x, dxs, dt, Kc<T>::EPSILON, hi_s);     // :94 (own element only)
+            sm.yxl[m] = euler_clamp(l, dxl, dt, T(1), xl_max);             // :95
+        }
+    }
+    const bool allsat = !__syncthreads_or((int)unsat);            // :90 (also: contributions complete)
+    if (!adaptive) {
+        // :149-153 — the update happens even when the pre-update state was all-satisfied.  No thread
+        // reads yv until the barrier below, so the in-place write is safe.
+        for (int i = tid; i < N; i += NT) sm.yv[i] = euler_clamp(sm.yv[i], small_dv<T>(f, i, sm.contrib), dt, T(-1), T(1));   // :96
+        __syncthreads();
+        return allsat;
+    }
+    if (allsat) return true;                                       // :122 — state untouched
+    for (int i = tid; i < N; i += NT) {
+        const T dv = small_dv<T>(f, i, sm.contrib);
+        sm.hv[i] = euler_clamp(sm.yv[i], dv, h, T(-1), T(1));      // :128
+        sm.fv[i] = euler_clamp(sm.yv[i], dv, dt, T(-1), T(1));     // :125
+    }
+    __syncthreads();
+    // ---- k2 = f(y_half); y_new = y_half + dt/2 k2; error vs y_full ---------------------------
+    U err = ErrBits<T>::NONE;
+    auto fold = [&](T e) { if (e == e) { const U b = ErrBits<T>::enc(e); if (b > err) err = b; } };   // NaN-ignoring max (:103)
+    for (int m = tid; m < M; m += NT) {
+        T dxs, dxl;
+        const T x = sm.hxs[m], l = sm.hxl[m];
+        small_clause<T>(f, m, sm.hv, x, l, zeta, sm.contrib, dxs, dxl);    // flag discarded (:129)
+        const T nx = euler_clamp(x, dxs, h, Kc<T>::EPSILON, hi_s);         // :130
+        const T nl = euler_clamp(l, dxl, h, T(1), xl_max);
+        fold(fabs(sm.fxs[m] - nx));
+        fold(fabs(sm.fxl[m] - nl));
+        sm.yxs[m] = nx;
+        sm.yxl[m] = nl;
+    }
+    __syncthreads();
+    for (int i = tid; i < N; i += NT) {
+        const T nv = euler_clamp(sm.hv[i], small_dv<T>(f, i, sm.contrib), h, T(-1), T(1));   // :130
+        fold(fabs(sm.fv[i] - nv));
+        sm.yv[i] = nv;
+    }
+    // block-wide NaN-ignoring max of the encoded errors
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const U other = __shfl_xor_sync(0xFFFFFFFFu, err, o); if (other > err) err = other; }
+    if ((tid & 31) == 0) sm.red[tid >> 5] = err;
+    __syncthreads();
+    U tot = ErrBits<T>::NONE;
+    for (int wq = 0; wq < NT / 32; ++wq) { const U o = sm.red[wq]; if (o > tot) tot = o; }
+    const T e = ErrBits<T>::dec(tot);
+    dt = rmax(rmin(dt * sqrt(tol / e), T(1e3)), T(0.0078125));     // :133-135
+    __syncthreads();                                               // red is rewritten by the next step
+    return false;
+}
+
+template <typename T, int NT>
+__device__ __forceinline__ void small_load(const SmallArgs<T>& a, const SmallSmem<T>& sm, int64_t rep) {
+    const int N = (int)a.f.N, M = (int)a.f.M;
+    for (int i = threadIdx.x; i < N; i += NT) sm.yv[i] = a.v[(int64_t)i * a.Rp + rep];
+    for (int m = threadIdx.x; m < M; m += NT) { sm.yxs[m] = a.xs[(int64_t)m * a.Rp + rep]; sm.yxl[m] = a.xl[(int64_t)m * a.Rp + rep]; }
+}
+template <typename T, int NT>
+__device__ __forceinline__ void small_store(const SmallArgs<T>& a, const SmallSmem<T>& sm, int64_t rep) {
+    const int N = (int)a.f.N, M = (int)a.f.M;
+    for (int i = threadIdx.x; i < N; i += NT) a.v[(int64_t)i * a.Rp + rep] = sm.yv[i];
+    for (int m = threadIdx.x; m < M; m += NT) { a.xs[(int64_t)m * a.Rp + rep] = sm.yxs[m]; a.xl[(int64_t)m * a.Rp + rep] = sm.yxl[m]; }
+}
+
+// `simulate` / `batch`: one CTA per replica, the whole chunk of steps with the replica resident.
 template <typename T, int NT>
 __global__ void __launch_bounds__(NT) k_solve_small(const SmallArgs<T> a) {
-    using U = typename ErrBits<T>::U;
     extern __shared__ __align__(16) unsigned char small_smem[];
-    const int N = (int)a.f.N, M = (int)a.f.M, L = (int)a.f.L;
-    const int tid = threadIdx.x;
+    const SmallSmem<T> sm(small_smem, (int)a.f.N, (int)a.f.M, (int)a.f.L, a.adaptive != 0);
     const int64_t rep = blockIdx.x;
-    T* yv = reinterpret_cast<T*>(small_smem);
-    T* yxs = yv + N;
-    T* yxl = yxs + M;
-    T* contrib = yxl + M;
-    T* hv = contrib + L;          // adaptive only: y_half, y_full
-    T* hxs = hv + N;
-    T* hxl = hxs + M;
-    T* fv = hxl + M;
-    T* fxs = fv + N;
-    T* fxl = fxs + M;
-    U* s_red = reinterpret_cast<U*>(small_smem + (((a.adaptive ? 3 : 1) * (size_t)(N + 2 * M) + (size_t)L) * sizeof(T) + 15) / 16 * 16);
-
-    const int64_t Rp = a.Rp;
-    for (int i = tid; i < N; i += NT) yv[i] = a.v[(int64_t)i * Rp + rep];
-    for (int m = tid; m < M; m += NT) { yxs[m] = a.xs[(int64_t)m * Rp + rep]; yxl[m] = a.xl[(int64_t)m * Rp + rep]; }
+    small_load<T, NT>(a, sm, rep);
     int32_t solved_at = a.solved_step[rep];
     T dt = a.adaptive ? a.dt_arr[rep] : a.dt;
-    const T hi_s = T(1) - Kc<T>::EPSILON;
     __syncthreads();
-
     for (int s = 0; s < a.nsteps; ++s) {
         if (solved_at >= 0 && (a.adaptive || a.freeze)) break;     // flagged replicas are done (adaptive) / frozen (fixed)
-        // ---- k1 = f(y) ------------------------------------------------------------------------
-        bool unsat = false;
-        const T h = T(0.5) * dt;
-        for (int m = tid; m < M; m += NT) {
-            T dxs, dxl;
-            const T x = yxs[m], l = yxl[m];
-            unsat = !small_clause<T>(a.f, m, yv, x, l, a.zeta, contrib, dxs, dxl) || unsat;
-            if (a.adaptive) {
-                hxs[m] = euler_clamp(x, dxs, h, Kc<T>::EPSILON, hi_s);      // :128
-                hxl[m] = euler_clamp(l, dxl, h, T(1), a.xl_max);
-                fxs[m] = euler_clamp(x, dxs, dt, Kc<T>::EPSILON, hi_s);     // :125
-                fxl[m] = euler_clamp(l, dxl, dt, T(1), a.xl_max);
-            } else {
-                yxs[m] = euler_clamp(x, dxs, dt, Kc<T>::EPSILON, hi_s);     // :94 (own element only)
-                yxl[m] = euler_clamp(l, dxl, dt, T(1), a.xl_max);           // :95
-            }
-        }
-        const bool allsat = !__syncthreads_or((int)unsat);         // :90 (also: contributions complete)
-        if (allsat && solved_at < 0) {
-            solved_at = a.step0 + s;
-            if (a.adaptive) break;                                 // :122 — state untouched
-        }
-        if (!a.adaptive) {
-            // :149-153 — the update happens even when the pre-update state was all-satisfied.  No thread
-            // reads yv until the barrier below, so the in-place write is safe.
-            for (int i = tid; i < N; i += NT) yv[i] = euler_clamp(yv[i], small_dv<T>(a.f, i, contrib), dt, T(-1), T(1));   // :96
-            __syncthreads();
-            continue;
-        }
-        for (int i = tid; i < N; i += NT) {
-            const T dv = small_dv<T>(a.f, i, contrib);
-            hv[i] = euler_clamp(yv[i], dv, h, T(-1), T(1));        // :128
-            fv[i] = euler_clamp(yv[i], dv, dt, T(-1), T(1));       // :125
-        }
-        __syncthreads();
-        // ---- k2 = f(y_half); y_new = y_half + dt/2 k2; error vs y_full ---------------------------
-        U err = ErrBits<T>::NONE;
-        auto fold = [&](T e) { if (e == e) { const U b = ErrBits<T>::enc(e); if (b > err) err = b; } };   // NaN-ignoring max (:103)
-        for (int m = tid; m < M; m += NT) {
-            T dxs, dxl;
-            const T x = hxs[m], l = hxl[m];
-            small_clause<T>(a.f, m, hv, x, l, a.zeta, contrib, dxs, dxl);   // flag discarded (:129)
-            const T nx = euler_clamp(x, dxs, h, Kc<T>::EPSILON, hi_s);      // :130
-            const T nl = euler_clamp(l, dxl, h, T(1), a.xl_max);
-            fold(fabs(fxs[m] - nx));
-            fold(fabs(fxl[m] - nl));
-            yxs[m] = nx;
-            yxl[m] = nl;
-        }
-        __syncthreads();
-        for (int i = tid; i < N; i += NT) {
-            const T nv = euler_clamp(hv[i], small_dv<T>(a.f, i, contrib), h, T(-1), T(1));   // :130
-            fold(fabs(fv[i] - nv));
-            yv[i] = nv;
-        }
-        // block-wide NaN-ignoring max of the encoded errors
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { const U other = __shfl_xor_sync(0xFFFFFFFFu, err, o); if (other > err) err = other; }
-        if ((tid & 31) == 0) s_red[tid >> 5] = err;
-        __syncthreads();
-        U tot = ErrBits<T>::NONE;
-        for (int wq = 0; wq < NT / 32; ++wq) { const U o = s_red[wq]; if (o > tot) tot = o; }
-        const T e = ErrBits<T>::dec(tot);
-        dt = rmax(rmin(dt * sqrt(a.tol / e), T(1e3)), T(0.0078125));   // :133-135
-        __syncthreads();                                               // s_red is rewritten next step
+        const bool allsat = small_step<T, NT>(a.f, sm, a.adaptive != 0, dt, a.tol, a.zeta, a.xl_max);
+        if (allsat && solved_at < 0) solved_at = a.step0 + s;
     }
-
-    for (int i = tid; i < N; i += NT) a.v[(int64_t)i * Rp + rep] = yv[i];
-    for (int m = tid; m < M; m += NT) { a.xs[(int64_t)m * Rp + rep] = yxs[m]; a.xl[(int64_t)m * Rp + rep] = yxl[m]; }
-    if (tid == 0) {
+    small_store<T, NT>(a, sm, rep);
+    if (threadIdx.x == 0) {
         a.solved_step[rep] = solved_at;
         if (a.adaptive) a.dt_arr[rep] = dt;
+    }
+}
+
+// Adaptive `simulate_inter` (system.rs:312-349) EXACTLY as the reference runs it: the replicas take their
+// steps one after the other inside every outer step and share ONE dt (`&mut dt`, system.rs:314 — quirk Q7),
+// so replica r+1's step size is the one replica r's error estimate just produced.  That is a sequential
+// dependency replica → replica: one CTA walks (outer step, replica) in order with the active replica
+// resident in shared memory; the loop ends after the first outer step in which some replica flagged.
+// dt_arr[0] carries the shared dt; solved_step[r] = the outer step on which r flagged.
+template <typename T, int NT>
+__global__ void __launch_bounds__(NT) k_inter_adaptive_small(const SmallArgs<T> a, int32_t* steps_done) {
+    extern __shared__ __align__(16) unsigned char small_smem[];
+    const SmallSmem<T> sm(small_smem, (int)a.f.N, (int)a.f.M, (int)a.f.L, true);
+    T dt = a.dt_arr[0];
+    int s = 0;
+    bool any = false;
+    for (; s < a.nsteps && !any; ++s) {
+        for (int64_t rep = 0; rep < a.R; ++rep) {
+            small_load<T, NT>(a, sm, rep);
+            __syncthreads();
+            const bool allsat = small_step<T, NT>(a.f, sm, true, dt, a.tol, a.zeta, a.xl_max);
+            if (allsat) {
+                any = true;
+                if (threadIdx.x == 0 && a.solved_step[rep] < 0) a.solved_step[rep] = a.step0 + s;
+            } else {
+                small_store<T, NT>(a, sm, rep);
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) {
+        a.dt_arr[0] = dt;
+        *steps_done = s;
     }
 }
 

@@ -172,9 +172,6 @@ void simulate_batch_impl(const odesat_formula* f, int64_t R, TH* v, TH* xs, TH* 
     ODESAT_REQUIRE(f != nullptr, "formula is NULL");
     ODESAT_REQUIRE(mode == ODESAT_MODE_BATCH || mode == ODESAT_MODE_INTER, "unknown mode");
     Resolved r = resolve(f, p);
-    if (mode == ODESAT_MODE_INTER && !r.fixed)
-        throw Error(ODESAT_EUNSUPPORTED, "adaptive `inter` shares one dt across replicas in the reference "
-                                         "(system.rs:314); only fixed-step inter is offered");
     if (mode == ODESAT_MODE_BATCH) ODESAT_REQUIRE(r.steps >= 0, "batch needs a step count (main.rs:96-97)");
     // the tile engine integrates fixed steps only: adaptive runs resolve AUTO to the gather engine
     const int eng = (!r.fixed && p->engine == ODESAT_ENGINE_AUTO) ? ODESAT_ENGINE_GATHER : p->engine;
@@ -185,7 +182,16 @@ void simulate_batch_impl(const odesat_formula* f, int64_t R, TH* v, TH* xs, TH* 
     if (!(v && xs && xl)) b->init(seed, replica_offset, !v, !xs, !xl, /*finalize=*/!(v || xs || xl));
     if (v || xs || xl) upload_host<TH>(*b, v, xs, xl, (v && xs && xl));
     std::vector<int64_t> solved;
-    const int64_t key = drive(*b, r, mode, solved);
+    int64_t key;
+    if (mode == ODESAT_MODE_INTER && !r.fixed) {
+        // adaptive inter: the replicas share ONE dt and step one after the other (system.rs:312-349, quirk Q7)
+        b->run_inter_adaptive(r.tol, r.zeta, r.steps);
+        solved.assign((size_t)R, -1);
+        b->status(solved.data(), nullptr);
+        key = b->first_key();
+    } else {
+        key = drive(*b, r, mode, solved);
+    }
     std::vector<uint8_t> ver((size_t)std::max<int64_t>(R, 1), 0);
     b->verify(ver.data());                                                       // cnf.rs:246-264
     int64_t win = -1, src = 0;

@@ -165,7 +165,8 @@ def simulate(state: State, formula: DeviceFormula, tolerance: Optional[float] = 
 def simulate_inter(states: Sequence[State], formula: DeviceFormula, tolerance: Optional[float] = None,
                    step_size: Optional[float] = None, steps: Optional[int] = None,
                    learning_rate: Optional[float] = None, *, chunk: int = 0, info: Optional[list] = None) -> List[bool]:
-    """system.rs:241-248 → Vec<bool>; fixed-step only (adaptive inter shares one dt, quirk Q7)."""
+    """system.rs:241-248 → Vec<bool>.  Without `step_size` the replicas share one adaptive dt and step
+    one after the other, exactly as the reference does (quirk Q7)."""
     R = len(states)
     v = np.ascontiguousarray(np.stack([s.v for s in states]), dtype=np.float64)
     xs = np.ascontiguousarray(np.stack([s.xs for s in states]), dtype=np.float64)

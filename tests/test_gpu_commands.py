@@ -37,5 +37,6 @@ def test_batch_and_inter_commands(golden_dir):
     res = commands.inter(str(golden_dir / "aim100_sat.cnf"), 128, step_number=6000, step_size=0.01, seed=2, log=lambda s: None)
     assert res.is_satisfiable and res.winner >= 0
     _check_render(res, golden_dir / "aim100_sat.cnf")
-    with pytest.raises(L.OdesatError):                                            # adaptive inter (quirk Q7) is refused
-        commands.inter(str(golden_dir / "aim100_sat.cnf"), 4, step_number=10, log=lambda s: None)
+    # without -s `inter` is adaptive with ONE dt shared by the replicas (quirk Q7) — offered, sequential like the reference
+    res = commands.inter(str(golden_dir / "aim100_sat.cnf"), 4, step_number=20000, seed=3, log=lambda s: None)
+    assert res.is_satisfiable and res.winner >= 0

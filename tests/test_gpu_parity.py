@@ -215,10 +215,6 @@ def test_simulate_batch_call_batch_and_inter(golden_dir):
     assert r4.winner == (int(np.argmax(exp)) if exp.any() else -1)
     if r4.winner >= 0:
         assert f.evaluate(r4.assignment)
-    # adaptive inter is refused, not silently approximated (quirk Q7)
-    with pytest.raises(L.OdesatError) as e:
-        B.simulate_batch(D, R, seed=1, steps=10, precision=L.F64, mode=L.MODE_INTER)
-    assert e.value.code == L.EUNSUPPORTED
 
 
 def test_unsat_fixture_never_flags(golden_dir):
@@ -320,3 +316,38 @@ def test_persistent_small_kernel_and_general_engine_agree_with_oracle(golden_dir
         assert eq(gst, ost)
         assert eq(gv, ov) and eq(gxs, oxs) and eq(gxl, oxl)
     b.close()
+
+
+@pytest.mark.parametrize("small", ["1", "0"])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_adaptive_inter_shares_one_dt_across_replicas_like_the_reference(golden_dir, monkeypatch, small, dtype):
+    """system.rs:312-349 (quirk Q7): in adaptive `inter` the replicas step one after the other inside an
+    outer step and share ONE dt.  Both device paths — the sequential one-CTA kernel (ODESAT_SMALL=1) and
+    the general engine stepping one replica at a time (ODESAT_SMALL=0) — reproduce the oracle exactly:
+    winner, outer steps, and the final state of EVERY replica (the loop stops right after the outer step
+    in which the first replica flags, as the reference's does)."""
+    monkeypatch.setenv("ODESAT_SMALL", small)
+    f = cnf.load_dimacs(str(golden_dir / "aim100_sat.cnf"))
+    D, F = both(f)
+    R = 5
+    prec = L.F64 if dtype == np.float64 else L.F32
+    for steps in (40, 4000):                                # a budget that runs out, and one that reaches a flag
+        v, xs, xl = F.init_batch(21, R, dtype)
+        gv, gxs, gxl = v.copy(), xs.copy(), xl.copy()
+        oa, owin, osteps = F.simulate_inter(v, xs, xl, tol=1e-3, steps=steps)
+        res = B.simulate_batch(D, R, gv, gxs, gxl, tolerance=1e-3, steps=steps, precision=prec, mode=L.MODE_INTER,
+                               write_back=True)
+        assert res.winner == owin and eq(res.assignment, oa)
+        assert eq(gv, v) and eq(gxs, xs) and eq(gxl, xl)
+        if owin >= 0:
+            assert res.steps_run == osteps and f.evaluate(res.assignment)
+    # the Rust-shaped mirror (f64 states in a list, as main.rs:348-360 builds them)
+    if dtype == np.float64:
+        v, xs, xl = F.init_batch(3, 3, np.float64)
+        states = [S.State(v[r].copy(), xs[r].copy(), xl[r].copy()) for r in range(3)]
+        info = []
+        got = S.simulate_inter(states, D, 1e-3, None, 3000, None, info=info)
+        oa, owin, osteps = F.simulate_inter(v, xs, xl, tol=1e-3, steps=3000)
+        assert [int(x) for x in got] == list(oa) and info[0][0] == owin
+        for r in range(3):
+            assert eq(states[r].v, v[r]) and eq(states[r].xs, xs[r]) and eq(states[r].xl, xl[r])
