@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""All five BASELINE.json configs on ONE B200 (multi-GPU configs: the per-GPU share), with the CPU
-oracle timed beside them on the box's host cores.  Prints one JSON line per config; the committed copy
-is profiles/r01_configs.jsonl.  (bench.py is the contract benchmark; this is the wider table.)
+"""All five BASELINE.json configs on ONE B200 (multi-GPU configs: the per-GPU share).  Prints one JSON
+line per config; the committed copy is profiles/r01_configs.jsonl.  (bench.py is the contract benchmark
+and the only place the CPU oracle is timed — `bench.py --workload hard|rand10k|… ` prints `cpu_baseline`;
+this script runs product code only.)
 
     python scripts/run_configs.py [--quick]
 """
@@ -21,7 +22,6 @@ from odesat_b200 import _lib as L                             # noqa: E402
 from odesat_b200 import batch as B                            # noqa: E402
 from odesat_b200 import cnf, commands                         # noqa: E402
 from odesat_b200.system import DeviceFormula                  # noqa: E402
-from oracle import oracle as O                                # noqa: E402
 
 GOLD = ROOT / "tests" / "golden"
 
@@ -35,7 +35,6 @@ def main():
     ap.add_argument("--quick", action="store_true")
     args = ap.parse_args()
     peak, _ = measured_peak()
-    cores = O.host_cores()
 
     # ---- configs[0]: tests/easy.cnf via `solve` (adaptive, -r 7) ---------------------------------
     times, steps, ok, tpre, tint = [], [], [], [], []
@@ -47,18 +46,9 @@ def main():
         ok.append(r.is_satisfiable)
         tpre.append(r.seconds_preprocess)
         tint.append(r.seconds_integrate)
-    f = cnf.load_dimacs(str(GOLD / "aim100_sat.cnf"))
-    OF = O.OracleFormula(f.varnum, f.clause_off, f.lits)
-    ct = []
-    for seed in range(8):
-        v = OF.init_v0(1, seed); xs = OF.init_short_term_memory(); xl = np.ones(OF.M)
-        t0 = time.perf_counter()
-        OF.simulate(v, xs, xl, tol=1e-3, steps=1_000_000)
-        ct.append(time.perf_counter() - t0)
     emit(config=0, what="easy.cnf `solve` adaptive -r 7 (8 seeds): preprocessing + GPU integration + trace replay, end to end",
          all_verified_sat=all(ok), steps_median=float(np.median(steps)), seconds_median_end_to_end=float(np.median(times)),
-         seconds_median_host_preprocessing_python=float(np.median(tpre)), seconds_median_upload_plus_gpu_integration=float(np.median(tint)),
-         cpu_oracle_seconds_median_unpreprocessed_integration_only=float(np.median(ct)))
+         seconds_median_host_preprocessing_python=float(np.median(tpre)), seconds_median_upload_plus_gpu_integration=float(np.median(tint)))
 
     # ---- configs[1]: tests/hard.cnf `batch -b 100 -n 1000 -s 0.01` --------------------------------
     fh = cnf.load_dimacs(str(GOLD / "aim100_unsat.cnf"))
@@ -70,17 +60,6 @@ def main():
         sec = time.perf_counter() - t0
         emit(config=1, what=f"hard.cnf batch -b 100 -n 1000 -s 0.01, {name}, one odesat_simulate_batch call (host in/out)",
              seconds=sec, clause_evals_per_s=1000 * 160 * 100 / sec, any_verified=bool(r.verified.any()), steps_run=int(r.steps_run))
-    OH = O.OracleFormula(fh.varnum, fh.clause_off, fh.lits)
-    v, xs, xl = OH.init_batch(1, 100)
-    t0 = time.perf_counter()
-    OH.batch_fixed(v, xs, xl, 0.01, fh.default_zeta(), 1000, freeze=True, nthreads=1)
-    s1 = time.perf_counter() - t0
-    v, xs, xl = OH.init_batch(1, 100)
-    t0 = time.perf_counter()
-    OH.batch_fixed(v, xs, xl, 0.01, fh.default_zeta(), 1000, freeze=True, nthreads=cores)
-    sn = time.perf_counter() - t0
-    emit(config=1, what="hard.cnf batch, CPU oracle f64", seconds_1_core=s1, seconds_all_cores=sn, cores=cores,
-         clause_evals_per_s_1_core=1.6e7 / s1, clause_evals_per_s_all_cores=1.6e7 / sn)
 
     # ---- configs[2..4]: throughput of the step loop, device-resident state -------------------------
     def throughput(cfg, what, f, R, prec, adaptive, steps, warm, sched=L.SCHED_BALANCED):
@@ -112,15 +91,6 @@ def main():
     f4 = cnf.random_ksat(50_000, 4.25, seed=20240615)
     for prec in (L.F32, L.F64):
         throughput(4, "random 3-SAT N=50k alpha=4.25, 2048 replicas (per-GPU share of 16384 over 8 GPUs), fixed step", f4, 2048, prec, False, 8 * k, 3)
-    # CPU oracle on a slice of config 2 for scale
-    OF2 = O.OracleFormula(f2.varnum, f2.clause_off, f2.lits)
-    Rc = cores * 2
-    v, xs, xl = OF2.init_batch(1, Rc)
-    t0 = time.perf_counter()
-    OF2.batch_fixed(v, xs, xl, 0.01, f2.default_zeta(), 50, freeze=False, nthreads=cores)
-    sec = time.perf_counter() - t0
-    emit(config=2, what=f"CPU oracle f64, {Rc} replicas x 50 steps on {cores} cores", clause_evals_per_s=50 * f2.n_clauses * Rc / sec, cores=cores)
-
 
 if __name__ == "__main__":
     main()
