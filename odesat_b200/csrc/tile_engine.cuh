@@ -748,7 +748,10 @@ template <typename T> struct TileEngine final : TileBase<T> {
                 auto l = levels_for(c);
                 double items = 0;
                 for (const auto& b : l->bucket) items += (double)((b.size() + c - 1) / c);
-                const double cost = items * (454.0 + c);
+                // width preference measured on B200 at the headline size (BALANCED, ms/step at 512/640/768/1024 threads:
+                // f32 0.611/0.596/0.588/0.603, f64 0.656/0.637/0.659/0.666): the widest CTA is not the fastest
+                const double pref = c == 1024 ? (sizeof(T) == 4 ? 1.12 : 1.25) : (c == 768 && sizeof(T) == 8 ? 1.10 : 1.0);
+                const double cost = items * (454.0 + c) * pref;
                 if (cost < best) { best = cost; nt = c; lv = l; }
             }
             if (!lv) { nt = 128; lv = levels_for(128); }
