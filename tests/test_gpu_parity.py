@@ -242,6 +242,13 @@ def test_steps_to_solution_distribution_256_seeds(golden_dir):
     assert stats.ks_2samp(a, b).pvalue > 0.01
     assert stats.mannwhitneyu(a, b).pvalue > 0.01
     assert (r32.solved_step >= 0).sum() > R // 8
+    # the throughput configuration (f32, BALANCED schedule: dv summed in colour order) draws from the same distribution
+    r32b = B.simulate_batch(D, R, seed=77, step_size=0.01, steps=steps, precision=L.F32, schedule=L.SCHED_BALANCED)
+    c = np.where(r32b.solved_step >= 0, r32b.solved_step, steps)
+    assert stats.ks_2samp(a, c).pvalue > 0.01 and stats.mannwhitneyu(a, c).pvalue > 0.01
+    # every emitted winner is verified exactly (cnf.rs:246-264), on the device and here on the host
+    for r in (r64, r32, r32b):
+        assert r.winner >= 0 and r.verified[r.winner] == 1 and f.evaluate(r.assignment)
 
 
 def test_error_paths(golden_dir):
