@@ -339,11 +339,8 @@ template <typename T> struct BatchImpl final : BatchBase {
     }
     int preferred_chunk() const override { return small_ok(true) ? 1024 : 32; }
     template <int NT> void launch_small_nt(const SmallArgs<T>& a, size_t smem) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            ODESAT_CUDA(cudaFuncSetAttribute(k_solve_small<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmem));
-            attr_set = true;
-        }
+        static uint64_t attr_devs = 0;   // per instantiation: devices on which the attribute is set
+        ensure_max_smem(k_solve_small<T, NT>, (int)kSmallSmem, attr_devs);
         k_solve_small<T, NT><<<(unsigned)R, NT, smem, stream>>>(a);
     }
     void run_small(bool adaptive, double dt, double tol, double zeta, int64_t n, int freeze) {

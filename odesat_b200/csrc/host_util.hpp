@@ -81,6 +81,18 @@ template <typename T> struct DevBuf {
     size_t bytes() const { return n * sizeof(T); }
 };
 
+// Opt a kernel into its large dynamic shared memory once per (kernel instantiation, device): the attribute
+// belongs to the device's copy of the function, so a second GPU used from the same process needs its own call.
+// `mask` is a function-local static of the caller.
+template <typename K> inline void ensure_max_smem(K kernel, int bytes, uint64_t& mask) {
+    int dev = 0;
+    ODESAT_CUDA(cudaGetDevice(&dev));
+    const uint64_t bit = uint64_t(1) << (dev & 63);
+    if (mask & bit) return;
+    ODESAT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    mask |= bit;
+}
+
 inline int64_t pad32(int64_t r) { return (r + 31) / 32 * 32; }
 
 }  // namespace odesat

@@ -401,11 +401,8 @@ template <typename T> struct ClusterTileEngine final : TileBase<T> {
     template <int NT, int D, int CL, bool STRICT> void launch(const CTileArgs<T>& a) {
         const size_t smem = smem_bytes(f.N, sched->n_items, CL, NT, D);
         auto kern = k_ctile_fixed<T, NT, D, CL, STRICT>;
-        static bool attr_set = false;   // per instantiation
-        if (!attr_set) {
-            ODESAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-            attr_set = true;
-        }
+        static uint64_t attr_devs = 0;   // per instantiation: devices on which the attribute is set
+        ensure_max_smem(kern, (int)kMaxSmem, attr_devs);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(R * CL), 1, 1);
         cfg.blockDim = dim3(NT, 1, 1);

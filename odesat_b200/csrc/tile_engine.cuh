@@ -802,11 +802,8 @@ template <typename T> struct TileEngine final : TileBase<T> {
 
     template <int NT, int D, bool STRICT> void launch(const TileArgs<T>& a) {
         const size_t smem = smem_bytes(f.N, sched->n_items, NT, D);
-        static bool attr_set = false;   // per instantiation
-        if (!attr_set) {
-            ODESAT_CUDA(cudaFuncSetAttribute(k_tile_fixed<T, NT, D, STRICT, (NT < 1024)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-            attr_set = true;
-        }
+        static uint64_t attr_devs = 0;   // per instantiation: devices on which the attribute is set
+        ensure_max_smem(k_tile_fixed<T, NT, D, STRICT, (NT < 1024)>, (int)kMaxSmem, attr_devs);
         k_tile_fixed<T, NT, D, STRICT, (NT < 1024)><<<(unsigned)tiles, NT, smem, stream>>>(a);
     }
     template <int NT> void launch_d(const TileArgs<T>& a, bool strict) {
@@ -820,11 +817,8 @@ template <typename T> struct TileEngine final : TileBase<T> {
         }
     }
     template <bool STRICT> void launch_small(const TileArgs<T>& a) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            ODESAT_CUDA(cudaFuncSetAttribute(k_tile_small<T, STRICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-            attr_set = true;
-        }
+        static uint64_t attr_devs = 0;   // per instantiation: devices on which the attribute is set
+        ensure_max_smem(k_tile_small<T, STRICT>, (int)kMaxSmem, attr_devs);
         k_tile_small<T, STRICT><<<(unsigned)tiles, 32, smem_small(f.N, sched->n_items), stream>>>(a);
     }
     void launch_nt(const TileArgs<T>& a, bool strict) {
