@@ -37,6 +37,9 @@ def workload(args):
     if args.workload == "rand10k":
         f = cnf.random_ksat(10_000, 4.3, seed=FORMULA_SEED)
         name = f"random 3-SAT N=10000 alpha=4.3 M=43000, {args.replicas} replicas/GPU, fixed step dt=0.01"
+    elif args.workload == "rand20k":
+        f = cnf.random_ksat(20_000, 4.3, seed=20240611 + 5)
+        name = f"random 3-SAT N=20000 alpha=4.3, {args.replicas} replicas/GPU, fixed step dt=0.01"
     elif args.workload == "rand50k":
         f = cnf.random_ksat(50_000, 4.25, seed=20240611 + 4)
         name = f"random 3-SAT N=50000 alpha=4.25, {args.replicas} replicas/GPU, fixed step dt=0.01"
@@ -396,7 +399,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="rand10k", choices=["rand10k", "rand50k", "rand1m", "hard"])
+    ap.add_argument("--workload", default="rand10k", choices=["rand10k", "rand20k", "rand50k", "rand1m", "hard"])
     ap.add_argument("--replicas", type=int, default=4096, help="replicas per GPU")
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--engine", default="auto", choices=["auto", "gather", "tile"])
