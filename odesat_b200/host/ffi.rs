@@ -96,7 +96,8 @@ pub fn simulate(state: &mut State, formula: &GpuFormula, tolerance: Option<f64>,
     a.into_iter().map(|x| x != 0).collect()
 }
 
-/// Drop-in for `system::simulate_inter` (system.rs:241-248); fixed step only.
+/// Drop-in for `system::simulate_inter` (system.rs:241-248): fixed step, or — `step_size = None` — adaptive
+/// with ONE dt shared by the replicas, stepped one after the other as the reference does (system.rs:312-349).
 pub fn simulate_inter(states: &mut Vec<State>, formula: &GpuFormula, tolerance: Option<f64>, step_size: Option<f64>,
                       steps: Option<usize>, learning_rate: Option<f64>) -> Vec<bool> {
     let (r, n, m) = (states.len(), formula.varnum, formula.n_clauses);
