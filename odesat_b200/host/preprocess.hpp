@@ -89,12 +89,37 @@ inline ClauseSet calculate_var_resolvents(const Index& idx, std::size_t variable
     return all;
 }
 
-inline void subsume_clauses(ClauseSet& clauses) {   // cnf.rs:521-539: drop proper supersets
-    std::vector<Clause> drop;
-    for (const Clause& c : clauses)
-        for (const Clause& p : clauses)
-            if (c != p && std::includes(c.begin(), c.end(), p.begin(), p.end())) { drop.push_back(c); break; }
-    for (const Clause& c : drop) clauses.erase(c);
+// cnf.rs:521-539: drop every clause that is a proper superset of another one.  The result does not depend on the
+// visiting order.  A proper superset is strictly longer, so clauses are visited by increasing length and each is
+// tested only against the shorter clauses filed under one of ITS literals (a subset's filing literal — its
+// smallest — must occur in the superset), with a 64-bit signature as a first filter.
+inline void subsume_clauses(ClauseSet& clauses) {
+    struct Item { const Clause* c; uint64_t sig; };
+    auto sig_of = [](const Clause& c) { uint64_t s = 0; for (Lit l : c) s |= uint64_t(1) << (l & 63u); return s; };
+    std::map<std::size_t, std::vector<Item>> by_len;
+    for (const Clause& c : clauses) by_len[c.size()].push_back(Item{&c, sig_of(c)});
+    std::map<Lit, std::vector<Item>> filed;
+    std::vector<Item> empties;                      // the empty clause is a subset of every clause
+    std::vector<const Clause*> drop;
+    for (auto& kv : by_len) {
+        for (const Item& it : kv.second) {
+            bool hit = !empties.empty() && !it.c->empty();
+            for (std::size_t k = 0; k < it.c->size() && !hit; ++k) {
+                auto f = filed.find((*it.c)[k]);
+                if (f == filed.end()) continue;
+                for (const Item& p : f->second)
+                    if ((p.sig & ~it.sig) == 0 && std::includes(it.c->begin(), it.c->end(), p.c->begin(), p.c->end())) { hit = true; break; }
+            }
+            if (hit) drop.push_back(it.c);
+        }
+        for (const Item& it : kv.second) {
+            if (it.c->empty()) empties.push_back(it);
+            else filed[it.c->front()].push_back(it);
+        }
+    }
+    std::vector<Clause> gone;
+    for (const Clause* c : drop) gone.push_back(*c);
+    for (const Clause& c : gone) clauses.erase(c);
 }
 
 inline bool is_blocked(const Clause& clause, const Index& idx, std::size_t* var) {   // cnf.rs:588-599

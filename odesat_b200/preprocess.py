@@ -62,35 +62,65 @@ def is_tautology(c: Clause) -> bool:
 
 def calculate_resolvents(idx: Index, clause: Clause, variable: int) -> List[Clause]:
     """cnf.rs:440-479: resolvents of `clause` on `variable`; tautological (w.r.t. `clause`) and
-    empty resolvents are dropped, exactly as the reference does."""
+    empty resolvents are dropped, exactly as the reference does.  (The reference walks both sets in
+    BTreeSet order; every caller uses the result as a set / under `all`, so the order is immaterial.)"""
     others = idx[variable][1] if variable in clause else idx[variable][0]
     base = frozenset(l for l in clause if abs(l) != variable)
+    neg_base = frozenset(-l for l in base)
     out: List[Clause] = []
-    for other in sorted_clauses(others):
-        combined = set(base)
-        for l in sorted_literals(other):
-            if abs(l) != variable:
-                if -l in base:
-                    combined.clear()
-                    break
-                combined.add(l)
+    for other in others:
+        rest = [l for l in other if abs(l) != variable]
+        if not neg_base.isdisjoint(rest):          # a literal of `other` contradicts one of `clause`: cleared
+            continue
+        combined = base.union(rest)
         if combined:
-            out.append(frozenset(combined))
+            out.append(combined)
     return out
 
 
 def calculate_var_resolvents(idx: Index, variable: int) -> Set[Clause]:
     """cnf.rs:481-498."""
     out: Set[Clause] = set()
-    for pc in sorted_clauses(idx[variable][0]):
+    for pc in idx[variable][0]:
         out.update(calculate_resolvents(idx, pc, variable))
     return out
 
 
 def subsume_clauses(clauses: Set[Clause]) -> None:
-    """cnf.rs:521-539: drop every clause that is a proper superset of another one."""
-    order = sorted_clauses(clauses)
-    drop = [c for c in order if any(c != p and c >= p for p in order)]
+    """cnf.rs:521-539: drop every clause that is a proper superset of another one.  The result does
+    not depend on the visiting order.  A proper superset is strictly longer, so clauses are visited by
+    increasing length and each one is tested only against the shorter clauses filed under one of ITS
+    literals (a subset's filing literal must occur in the superset), as bit masks."""
+    bit: Dict[int, int] = {}
+    by_len: Dict[int, List[Tuple[int, Clause]]] = {}
+    for c in clauses:
+        m = 0
+        for l in c:
+            b = bit.get(l)
+            if b is None:
+                b = bit[l] = 1 << len(bit)
+            m |= b
+        by_len.setdefault(len(c), []).append((m, c))
+    filed: Dict[int, List[int]] = {}           # literal → masks of the shorter clauses filed under it
+    drop: List[Clause] = []
+    for n in sorted(by_len):
+        for m, c in by_len[n]:
+            hit = False
+            for l in c:
+                for p in filed.get(l, ()):
+                    if p & m == p:
+                        hit = True
+                        break
+                if hit:
+                    break
+            if hit:
+                drop.append(c)
+        for m, c in by_len[n]:
+            if c:
+                filed.setdefault(min(c), []).append(m)
+            else:                               # the empty clause is a subset of every clause
+                for l in bit:
+                    filed.setdefault(l, []).append(m)
     for c in drop:
         clauses.discard(c)
 
