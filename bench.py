@@ -185,6 +185,19 @@ def traffic_for(engine_name, precision, schedule, steps, launches):
     return None
 
 
+def cpu_sample_adaptive(f, cores):
+    """Single-instance adaptive workload: the oracle's `simulate` on ONE core (the reference is single-threaded)."""
+    from oracle import oracle as O
+    F = O.OracleFormula(f.varnum, f.clause_off, f.lits)
+    v = F.init_v0(RUN_SEED, 0); xs = F.init_short_term_memory(); xl = np.ones(F.M)
+    F.simulate(v, xs, xl, tol=1e-3, steps=2)                                                 # warm
+    steps = 8
+    t0 = time.perf_counter()
+    F.simulate(v, xs, xl, tol=1e-3, steps=steps)
+    sec = time.perf_counter() - t0
+    return steps * f.n_clauses / sec, f"1 instance x {steps} adaptive steps (2 RHS evaluations each), f64, 1 thread, {sec:.2f} s"
+
+
 def cpu_sample(f, args, cores, steps_hint=None):
     """Times the oracle (a C++ restatement of system.rs, f64, one replica per thread-slot — the way
     main.rs:278-308 runs `batch`, spread over the host cores) on a bounded sample of the workload."""
@@ -304,7 +317,7 @@ def run_gpu(args):
     flagged = int((st >= 0).sum())
     b.close()
     other = None
-    if args.quick or adaptive:
+    if args.quick:
         if rank == 0:
             print(json.dumps({"quick": True, "workload": args.workload, "engine": eng_name, "schedule": args.schedule,
                               "precision": args.precision, "ms_per_step": ms_max / args.steps, "value": value,
@@ -336,7 +349,8 @@ def run_gpu(args):
         # inputs = the random v0 of every replica, from pinned host memory (main.rs:283-289 draws them
         # on the host); xs0 / xl0 are functions of the formula (init_short_term_memory, ones) and are
         # built on the device, as `batch` builds them from the formula
-        return B.simulate_batch(F, R, hv.data_ptr(), None, None, step_size=DT, steps=e2e_steps,
+        return B.simulate_batch(F, R, hv.data_ptr(), None, None, step_size=None if adaptive else DT,
+                                tolerance=1e-3 if adaptive else None, steps=e2e_steps,
                                 precision=prec, engine=engine, schedule=sched, mode=L.MODE_BATCH, write_back=False,
                                 chunk=max(32, e2e_steps))
     e2e_call()                                                    # warm (allocator, schedule cache)
@@ -359,7 +373,13 @@ def run_gpu(args):
     if rank == 0:
         from oracle import oracle as O
         cores = O.host_cores()
-        cpu_val, cpu_sample_desc = cpu_sample(f, args, cores) if world == 1 else (None, None)
+        if world > 1:
+            cpu_val, cpu_sample_desc = None, None
+        elif adaptive:
+            cpu_val, cpu_sample_desc = cpu_sample_adaptive(f, cores)
+            cores = 1
+        else:
+            cpu_val, cpu_sample_desc = cpu_sample(f, args, cores)
         out = {
             "metric": "clause-evals/sec", "value": value, "unit": "clause-evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
@@ -368,7 +388,8 @@ def run_gpu(args):
             "config": {"workload": name, "replicas_per_gpu": R, "replicas_total": R * world, "N": f.varnum,
                        "M": f.n_clauses, "engine": eng_name, "schedule": args.schedule, "formula_seed": FORMULA_SEED,
                        "parallelism": f"replica-sharded x{world}, no data-path collective",
-                       "l2": f"state {bytes_step / 2 / 1e6:.0f} MB per GPU is larger than L2 (126 MB); no flush needed",
+                       "l2": (f"state {bytes_step / 2 / 1e6:.0f} MB per GPU is larger than L2 (126 MB); no flush needed" if bytes_step / 2 > 126e6 else
+                              f"state {bytes_step / 2 / 1e6:.1f} MB per GPU fits in L2 (126 MB) and is NOT flushed between steps: a step's input is the previous step's output by construction"),
                        "flagged_replicas": flagged, "other_schedule_same_run": other,
                        "e2e_call": f"one odesat_simulate_batch call of {e2e_steps} steps per GPU: v0 of every replica "
                                    "from pinned host memory in; per-replica flags, exact verification and the "
