@@ -30,3 +30,16 @@ def random_state(rng, N, M, dtype=np.float64, R=None):
     xs = rng.uniform(0.001, 0.999, size=shape_m).astype(dtype)
     xl = rng.uniform(1.0, 50.0, size=shape_m).astype(dtype)
     return np.ascontiguousarray(v), np.ascontiguousarray(xs), np.ascontiguousarray(xl)
+
+
+def repeated_var_formula(seed: int, n_vars: int = 60, n_clauses: int = 300) -> cnf.Formula:
+    """Uniform 3-literal clauses in which a variable may repeat inside a clause, also with both signs
+    (x ∨ ¬x ∨ y): uniform length sends it to the streaming clause kernel, the repeats keep it off the
+    tile engine, and the summation order inside a clause matters for dv."""
+    rng = np.random.default_rng(seed)
+    var = rng.integers(1, n_vars + 1, size=(n_clauses, 3))
+    var[::5, 1] = var[::5, 0]                       # force repeats
+    sign = rng.integers(0, 2, size=(n_clauses, 3)) * 2 - 1
+    lits = (var * sign).astype(np.int32).reshape(-1)
+    off = np.arange(n_clauses + 1, dtype=np.int64) * 3
+    return cnf.Formula(n_vars, off, lits, {})

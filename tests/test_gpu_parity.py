@@ -12,7 +12,7 @@ from odesat_b200 import cnf
 from odesat_b200 import system as S
 from oracle import oracle as O
 
-from helpers import ragged_formula, random_state
+from helpers import ragged_formula, random_state, repeated_var_formula
 
 pytestmark = pytest.mark.gpu
 
@@ -31,6 +31,7 @@ FORMULAS = {
     "rand3": lambda g: cnf.random_ksat(300, 4.3, seed=4),
     "rand4": lambda g: cnf.random_ksat(120, 9.0, seed=5, k=4),
     "ragged": lambda g: ragged_formula(3),
+    "repeat3": lambda g: repeated_var_formula(9),
 }
 
 
@@ -289,7 +290,7 @@ def test_large_single_instance_adaptive_and_fixed(dtype):
 
 
 @pytest.mark.parametrize("small", ["1", "0"])
-@pytest.mark.parametrize("name", ["aim_sat", "ragged", "rand4"])
+@pytest.mark.parametrize("name", ["aim_sat", "ragged", "rand4", "repeat3"])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_persistent_small_kernel_and_general_engine_agree_with_oracle(golden_dir, monkeypatch, small, name, dtype):
     """The persistent one-CTA-per-replica kernel (kernels_small.cuh; ODESAT_SMALL=1, default) and the
