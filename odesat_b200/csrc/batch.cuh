@@ -215,6 +215,7 @@ template <typename T> struct BatchImpl final : BatchBase {
             ++launches;
         }
         ODESAT_CUDA(cudaGetLastError());
+        if (gen_v) v_in_range = true;                    // v0 ∈ [-1, 1) by construction
         if (tile && !finalize) { canon_ahead = true; canon_current = false; return; }
         canon_to_tile();
         ODESAT_CUDA(cudaStreamSynchronize(stream));
@@ -230,6 +231,7 @@ template <typename T> struct BatchImpl final : BatchBase {
         ODESAT_CUDA(cudaGetLastError());
         canon_to_tile();
         ODESAT_CUDA(cudaStreamSynchronize(stream));
+        if (v && !tile) check_v_range();
     }
 
     void download(void* v, void* xs, void* xl) override {
@@ -249,6 +251,23 @@ template <typename T> struct BatchImpl final : BatchBase {
     // f32): 7.7 / 6.1 / 4.7 / 4.1 / 3.9 ms per step for S = 16 / 32 / 128 / 256 / 512 against 3.74 ms
     // unslabbed — the small launches are instruction- and latency-bound and lose more than the L2
     // residency gains, so the default is one launch pair over the whole batch.
+    // the streaming clause kernel may use the tile kernel's shorter arithmetic once every v is known to be finite in
+    // [-1, 1] (true after any step: system.rs:96 clamps; checked on upload) and zeta is finite
+    bool v_in_range = false;
+    DevBuf<unsigned> range_flag;
+    void check_v_range() {
+        if (tile || R == 0 || f->N == 0) { v_in_range = true; return; }
+        if (!range_flag.p) range_flag.alloc(1, &dev_bytes);
+        ODESAT_CUDA(cudaMemsetAsync(range_flag.p, 0, 4, stream));
+        dim3 g, b;
+        geom(f->N, g, b);
+        k_check_range<T><<<g, b, 0, stream>>>(S[cur].v.p, f->N, R, Rp, range_flag.p);
+        ++launches;
+        unsigned h = 1;
+        ODESAT_CUDA(cudaMemcpyAsync(&h, range_flag.p, 4, cudaMemcpyDeviceToHost, stream));
+        ODESAT_CUDA(cudaStreamSynchronize(stream));
+        v_in_range = h == 0;
+    }
     int64_t slab = 0;        // 0 = whole batch in one launch pair
     int slab_steps = 1;
     void pick_slab() {
@@ -272,6 +291,8 @@ template <typename T> struct BatchImpl final : BatchBase {
         a.rep1 = R;
         a.cstride = (slabbed && slab > 0) ? slab : Rp;
         a.zeta = (T)zeta;
+        a.fast = (v_in_range && std::isfinite(zeta)) ? 1 : 0;
+        if (const char* e = std::getenv("ODESAT_GATHER_FAST")) { if (e[0] == '0') a.fast = 0; }
         if (const char* e = std::getenv("ODESAT_GATHER_L2HINTS")) a.l2_hints = std::atoi(e);
         a.xl_max = T(1e4) * T(f->M);
         a.solved_step = solved.p;
@@ -406,6 +427,7 @@ template <typename T> struct BatchImpl final : BatchBase {
             a.step = (int32_t)at_step;
             a.freeze = freeze;
             launch_gather<G_FIXED>(a);
+            v_in_range = true;                           // every stepped v is clamped (system.rs:96); frozen replicas were clamped before
         };
         if (slab > 0) {
             for (int64_t done = 0; done < n; done += slab_steps) {
@@ -455,6 +477,7 @@ template <typename T> struct BatchImpl final : BatchBase {
             }
             cur = 1 - cur;
             ++step;
+            v_in_range = true;   // stepped replicas are clamped; flagged ones are never evaluated again
         }
         time_end(ms);
     }
@@ -527,6 +550,7 @@ template <typename T> struct BatchImpl final : BatchBase {
             }
             cur = 1 - cur;
             ++done;
+            v_in_range = true;
             if (first_key() != NONE) break;
         }
         ODESAT_CUDA(cudaMemcpyAsync(dtv.p, dt_shared.p, sizeof(T), cudaMemcpyDeviceToDevice, stream));

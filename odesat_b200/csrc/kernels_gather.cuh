@@ -30,6 +30,8 @@ template <typename T> struct GatherArgs {
     int64_t cstride = 0;          // row stride of contrib (Rp, or the slab width: contrib[slot][rep - rep0])
     int rows_per_thread = 8;      // rows a thread walks per launch: fewer, fatter blocks
     int l2_hints = 0;             // evict-first on the once-per-step streams, evict-last on the v gathers
+    int fast = 0;                 // streaming clause kernel: every v is finite in [-1, 1] and zeta is finite, so the
+                                  // tile kernel's shorter arithmetic (bit-identical on that domain) may be used
     const T *v = nullptr, *xs = nullptr, *xl = nullptr;   // state the RHS is evaluated on
     T *ov = nullptr, *oxs = nullptr, *oxl = nullptr;      // FIXED: y(t+1) (may alias the inputs); DERIV: dy; A: y_half; B: y_new
     T *fv = nullptr, *fxs = nullptr, *fxl = nullptr;      // A: y_full (out); B: y_full (in)
@@ -239,6 +241,17 @@ __global__ void __launch_bounds__(256) k_clause_phase(const GatherArgs<T> a) {
     }
 }
 
+__device__ __forceinline__ float gfma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double gfma(double a, double b, double c) { return __fma_rn(a, b, c); }
+
+// any |v| > 1 or NaN in the batch? (decides whether the first step may use the fast arithmetic)
+template <typename T> __global__ void k_check_range(const T* v, int64_t N, int64_t R, int64_t Rp, unsigned* flag) {
+    const int64_t rep = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+    const int64_t row = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
+    if (rep >= R || row >= N) return;
+    if (!(fabs(v[row * Rp + rep]) <= T(1))) *flag = 1u;
+}
+
 // ---- streaming clause phase (uniform 3-literal clauses) -------------------------------------------
 // The plain kernel above is latency-bound: literal load → v gather → memory load are three
 // dependent round trips per row (ncu: long-scoreboard stalls 16–17 cycles per issued instruction,
@@ -360,37 +373,66 @@ __global__ void __launch_bounds__(256) k_clause_stream(const GatherArgs<T> a) {
         }
         xs_m = *reinterpret_cast<const RVec<T, V>*>(cell(r, 3));
         xl_m = *reinterpret_cast<const RVec<T, V>*>(cell(r, 4));
-        T mn[V], sm[V];
+        T mn[V], sm[V], c[V];
+        if (a.fast) {
+            // Fast arithmetic (see clause_math in tile_engine.cuh): 1 − q·v as one exact FMA, min / second-min as a
+            // 5-op network, q·((0.5·xl·xs)·sel) for the addend, rigidity term dropped (identically ±0, quirk Q1).
+            // Bit-identical sums on the domain v ∈ [-1, 1] finite, zeta finite.
+            T av[3][V];
 #pragma unroll
-        for (int u = 0; u < V; ++u) { mn[u] = inf_v<T>(); sm[u] = inf_v<T>(); }
+            for (int j = 0; j < 3; ++j)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {                              // :46-57
-#pragma unroll
-            for (int u = 0; u < V; ++u) {
-                const T val = T(1) - qs[j] * vis[j].x[u];          // :49
-                if (val < mn[u]) { sm[u] = mn[u]; mn[u] = val; }   // :50-52
-                else if (val < sm[u]) { sm[u] = val; }             // :53-55
-            }
-        }
-        T c[V], w[V], rg[V];
-#pragma unroll
-        for (int u = 0; u < V; ++u) {
-            c[u] = T(0.5) * mn[u];                                 // :60
-            w[u] = xl_m.x[u] * xs_m.x[u];
-            rg[u] = (T(1) + a.zeta * xl_m.x[u]) * (T(1) - xs_m.x[u]);
-        }
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {                              // :62-81
-            RVec<T, V> t;
+                for (int u = 0; u < V; ++u) av[j][u] = gfma(-qs[j], vis[j].x[u], T(1));
 #pragma unroll
             for (int u = 0; u < V; ++u) {
-                const T val = T(1) - qs[j] * vis[j].x[u];
-                const T g = (T(0.5) * qs[j]) * ((val != mn[u]) ? mn[u] : sm[u]);       // :64-70
-                const T rr = (c[u] == val) ? T(0.5) * (qs[j] - vis[j].x[u]) : T(0);    // :73-77
-                t.x[u] = w[u] * g + rg[u] * rr;                                        // the addend of :80
+                const T lo = rmin(av[0][u], av[1][u]), hi = rmax(av[0][u], av[1][u]);
+                mn[u] = rmin(lo, av[2][u]);
+                sm[u] = rmax(lo, rmin(hi, av[2][u]));
+                c[u] = T(0.5) * mn[u];                             // :60
             }
-            if (a.l2_hints) vstore_cs<T, V>(a.contrib + (mrow[r] * 3 + j) * a.cstride + (rep - a.rep0), t);
-            else vstore<T, V>(a.contrib + (mrow[r] * 3 + j) * a.cstride + (rep - a.rep0), t);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                RVec<T, V> t;
+#pragma unroll
+                for (int u = 0; u < V; ++u) {
+                    const T h = T(0.5) * (xl_m.x[u] * xs_m.x[u]);
+                    t.x[u] = gfma(h * ((av[j][u] != mn[u]) ? mn[u] : sm[u]), qs[j], T(0));   // :64-70, :80
+                }
+                if (a.l2_hints) vstore_cs<T, V>(a.contrib + (mrow[r] * 3 + j) * a.cstride + (rep - a.rep0), t);
+                else vstore<T, V>(a.contrib + (mrow[r] * 3 + j) * a.cstride + (rep - a.rep0), t);
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < V; ++u) { mn[u] = inf_v<T>(); sm[u] = inf_v<T>(); }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {                              // :46-57
+#pragma unroll
+                for (int u = 0; u < V; ++u) {
+                    const T val = T(1) - qs[j] * vis[j].x[u];          // :49
+                    if (val < mn[u]) { sm[u] = mn[u]; mn[u] = val; }   // :50-52
+                    else if (val < sm[u]) { sm[u] = val; }             // :53-55
+                }
+            }
+            T w[V], rg[V];
+#pragma unroll
+            for (int u = 0; u < V; ++u) {
+                c[u] = T(0.5) * mn[u];                                 // :60
+                w[u] = xl_m.x[u] * xs_m.x[u];
+                rg[u] = (T(1) + a.zeta * xl_m.x[u]) * (T(1) - xs_m.x[u]);
+            }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {                              // :62-81
+                RVec<T, V> t;
+#pragma unroll
+                for (int u = 0; u < V; ++u) {
+                    const T val = T(1) - qs[j] * vis[j].x[u];
+                    const T g = (T(0.5) * qs[j]) * ((val != mn[u]) ? mn[u] : sm[u]);       // :64-70
+                    const T rr = (c[u] == val) ? T(0.5) * (qs[j] - vis[j].x[u]) : T(0);    // :73-77
+                    t.x[u] = w[u] * g + rg[u] * rr;                                        // the addend of :80
+                }
+                if (a.l2_hints) vstore_cs<T, V>(a.contrib + (mrow[r] * 3 + j) * a.cstride + (rep - a.rep0), t);
+                else vstore<T, V>(a.contrib + (mrow[r] * 3 + j) * a.cstride + (rep - a.rep0), t);
+            }
         }
         const T hi_s = T(1) - Kc<T>::EPSILON;
         RVec<T, V> o1, o2, f1, f2;
