@@ -204,6 +204,22 @@ template <typename T> struct BatchImpl final : BatchBase {
 
     void init(uint64_t seed, int64_t replica_offset, bool gen_v, bool gen_xs, bool gen_xl, bool finalize = true) override {
         StateBuf<T>& s = canon();
+        if (tile && tile->has_direct() && gen_xs && gen_xl && !canon_ahead && R > 0) {
+            // memories straight into the tile layout; v (if generated) through the canonical scratch and a v-only
+            // import — no full-state layout conversion.  When !gen_v the tile keeps its v (or upload(v) follows).
+            launches += tile->init_mem(f->dev.xs0);
+            if (gen_v && f->N > 0) {
+                dim3 g, b;
+                geom(f->N, g, b);
+                k_init_state<T><<<g, b, 0, stream>>>(s.v.p, s.xs.p, s.xl.p, f->dev.xs0, f->N, f->M, R, Rp, seed, replica_offset, 1, 0, 0);
+                ++launches;
+                launches += tile->import_v(s.v.p, Rp);
+            }
+            canon_current = false;
+            ODESAT_CUDA(cudaStreamSynchronize(stream));
+            ODESAT_CUDA(cudaGetLastError());
+            return;
+        }
         if (tile && !(gen_v && gen_xs && gen_xl) && !finalize) {
             // the caller uploads the arrays that are not generated here: nothing of the old state survives
         } else if (tile && !(gen_v && gen_xs && gen_xl)) tile_to_canon();
@@ -224,6 +240,14 @@ template <typename T> struct BatchImpl final : BatchBase {
     void upload(const void* v, const void* xs, const void* xl, bool reset) override {
         if (reset) reset_control();
         StateBuf<T>& s = canon();
+        if (tile && tile->has_direct() && v && !xs && !xl && !canon_ahead && R > 0) {   // v only: the tile keeps its memories
+            put(v, s.v.p, f->N);
+            launches += tile->import_v(s.v.p, Rp);
+            canon_current = false;
+            ODESAT_CUDA(cudaStreamSynchronize(stream));
+            ODESAT_CUDA(cudaGetLastError());
+            return;
+        }
         if (tile && !(v && xs && xl)) tile_to_canon();
         if (v) put(v, s.v.p, f->N);
         if (xs) put(xs, s.xs.p, f->M);
@@ -585,12 +609,18 @@ template <typename T> struct BatchImpl final : BatchBase {
 
     void verify(uint8_t* out) override {
         if (R == 0) return;
-        tile_to_canon();
-        StateBuf<T>& s = canon();
         DevBuf<uint32_t> bad;
         bad.alloc((size_t)R);
         ODESAT_CUDA(cudaMemsetAsync(bad.p, 0, bad.bytes(), stream));
-        if (f->M > 0) {
+        bool done = false;
+        if (tile && tile->has_direct() && !canon_ahead && !canon_current && f->M > 0) {
+            const int64_t n = tile->verify_direct(bad.p);   // on the tile layout: no export
+            launches += n;
+            done = n > 0;
+        }
+        if (!done) tile_to_canon();
+        StateBuf<T>& s = canon();
+        if (f->M > 0 && !done) {
             dim3 g, b;
             geom(f->M, g, b);
             k_verify<T><<<g, b, 0, stream>>>(f->dev, s.v.p, R, Rp, bad.p);
@@ -606,11 +636,16 @@ template <typename T> struct BatchImpl final : BatchBase {
     void assignment(int64_t r, uint8_t* out) override {
         ODESAT_REQUIRE(r >= 0 && r < R, "replica index out of range");
         if (f->N == 0) return;
-        tile_to_canon();
-        StateBuf<T>& s = canon();
         if (small8.n < (size_t)f->N) small8.alloc((size_t)f->N, &dev_bytes);
-        k_assignment<T><<<(unsigned)((f->N + 255) / 256), 256, 0, stream>>>(s.v.p, f->N, Rp, r, small8.p);
-        ++launches;
+        int64_t direct = 0;
+        if (tile && tile->has_direct() && !canon_ahead && !canon_current) direct = tile->assignment_direct(r, small8.p);
+        launches += direct;
+        if (direct == 0) {
+            tile_to_canon();
+            StateBuf<T>& s = canon();
+            k_assignment<T><<<(unsigned)((f->N + 255) / 256), 256, 0, stream>>>(s.v.p, f->N, Rp, r, small8.p);
+            ++launches;
+        }
         ODESAT_CUDA(cudaMemcpyAsync(out, small8.p, (size_t)f->N, cudaMemcpyDeviceToHost, stream));
         ODESAT_CUDA(cudaStreamSynchronize(stream));
         ODESAT_CUDA(cudaGetLastError());

@@ -638,6 +638,83 @@ __global__ void k_tile_export(T* __restrict__ v, T* __restrict__ xs, T* __restri
     }
 }
 
+// ---- tile-layout shortcuts of the e2e path (no canonical round trip) ----------------------------------
+// xs = xs0 (system.rs:362-372), xl = 1 (main.rs:287) for every replica, written straight into the slot order.
+template <typename T>
+__global__ void k_tile_init_mem(const int8_t* __restrict__ xs0, const int32_t* __restrict__ perm,
+                                typename TileTraits<T>::Mem* __restrict__ mem, int64_t Mpad, int64_t tiles) {
+    constexpr int W = TileTraits<T>::W;
+    using IO = RowIO<T, W>;
+    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t tile = blockIdx.y;
+    if (slot >= Mpad || tile >= tiles) return;
+    const int m = perm[slot];
+    T a[W], b[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) { a[w] = m >= 0 ? (T)xs0[m] : T(0); b[w] = m >= 0 ? T(1) : T(0); }
+    mem[tile * Mpad + slot] = IO::pack_mem(a, b);
+}
+// canonical v[row][Rp] → vt[tile][row][W] through a shared-memory transpose (both sides coalesced)
+template <typename T>
+__global__ void k_tile_import_v(const T* __restrict__ v, int64_t Rp, int64_t R, int64_t N, T* __restrict__ vt, int64_t tiles,
+                                unsigned* __restrict__ out_of_range) {
+    constexpr int W = TileTraits<T>::W;
+    __shared__ T t[32][33];
+    const int64_t x0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+    bool bad = false;
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        const int64_t row = x0 + k, r = r0 + threadIdx.x;
+        const T x = (row < N && r < R) ? v[row * Rp + r] : T(0);
+        t[k][threadIdx.x] = x;
+        bad = bad || !(fabs(x) <= T(1));
+    }
+    if (bad) *out_of_range = 1u;
+    __syncthreads();
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        const int64_t r = r0 + k, row = x0 + threadIdx.x;
+        if (row < N && r < tiles * W) vt[((r / W) * N + row) * W + (r % W)] = t[threadIdx.x][k];
+    }
+}
+// cnf.rs:246-264 for the replicas of one tile with the thresholded v in shared memory (one byte per variable,
+// bit w = v_w > 0); clauses come from the packed slot table.
+template <typename T>
+__global__ void __launch_bounds__(512) k_tile_verify(const T* __restrict__ vt, const uint64_t* __restrict__ entry,
+                                                     const int32_t* __restrict__ perm, int64_t N, int64_t Mpad, int64_t R,
+                                                     uint32_t* __restrict__ bad) {
+    constexpr int W = TileTraits<T>::W;
+    extern __shared__ __align__(16) unsigned char vbits[];
+    const int64_t tile = blockIdx.x;
+    const T* my = vt + tile * N * W;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        unsigned b = 0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) b |= (my[(int64_t)i * W + w] > T(0) ? 1u : 0u) << w;   // system.rs:238
+        vbits[i] = (unsigned char)b;
+    }
+    __syncthreads();
+    unsigned falsified = 0;   // bit w: some clause of replica w is falsified
+    const uint2* e2 = reinterpret_cast<const uint2*>(entry);
+    for (int64_t slot = threadIdx.x; slot < Mpad; slot += blockDim.x) {
+        if (perm[slot] < 0) continue;
+        const uint2 e = e2[slot];
+        const unsigned i0 = (e.x & 0x3FFF0u) >> 4, i1 = ((e.x >> 14) & 0x3FFF0u) >> 4, i2 = (e.y & 0x3FFF0u) >> 4;
+        const unsigned n0 = (e.y >> 24) & 1u ? 0xFFu : 0u, n1 = (e.y >> 25) & 1u ? 0xFFu : 0u, n2 = (e.y >> 26) & 1u ? 0xFFu : 0u;
+        const unsigned sat = (vbits[i0] ^ n0) | (vbits[i1] ^ n1) | (vbits[i2] ^ n2);
+        falsified |= ~sat;
+    }
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        const int any = __syncthreads_or((int)((falsified >> w) & 1u));
+        if (threadIdx.x == 0 && tile * W + w < R) bad[tile * W + w] = any ? 1u : 0u;
+    }
+}
+template <typename T>
+__global__ void k_tile_assignment(const T* __restrict__ vt, int64_t N, int64_t rep, uint8_t* __restrict__ out) {
+    constexpr int W = TileTraits<T>::W;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) out[i] = vt[((rep / W) * N + i) * W + (rep % W)] > T(0) ? 1 : 0;
+}
+
 // What BatchImpl needs from a shared-memory-resident engine (k_tile_fixed / k_tile_small here,
 // the thread-block-cluster variant in tile_cluster.cuh).
 template <typename T> struct TileBase {
@@ -646,6 +723,12 @@ template <typename T> struct TileBase {
     virtual int64_t import_state(const T* v, const T* xs, const T* xl, int64_t Rp) = 0;   // canonical [row][Rp] → tile layout
     virtual int64_t export_state(T* v, T* xs, T* xl, int64_t Rp) = 0;
     virtual int64_t run_fixed(T dt, T zeta, int64_t n, int freeze, int32_t* solved, int64_t step0) = 0;   // → launches
+    // Optional shortcuts that work on the tile layout directly (no canonical round trip); 0 = not offered.
+    virtual bool has_direct() const { return false; }
+    virtual int64_t init_mem(const int8_t* /*xs0*/) { return 0; }                                   // xs = xs0, xl = 1 for every replica
+    virtual int64_t import_v(const T* /*v*/, int64_t /*Rp*/) { return 0; }                          // canonical v only
+    virtual int64_t verify_direct(uint32_t* /*bad*/) { return 0; }                                  // bad[r] = some clause falsified
+    virtual int64_t assignment_direct(int64_t /*r*/, uint8_t* /*out_dev*/) { return 0; }            // out[i] = v_i > 0
 };
 
 template <typename T> struct TileEngine final : TileBase<T> {
@@ -796,6 +879,36 @@ template <typename T> struct TileEngine final : TileBase<T> {
         dim3 g, b;
         geom(f.N + sched->Mpad, g, b);
         k_tile_export<T><<<g, b, 0, stream>>>(v, xs, xl, Rp, R, f.N, sched->Mpad, sched->d_perm.p, vt.p, mem.p, tiles);
+        ODESAT_CUDA(cudaGetLastError());
+        return 1;
+    }
+
+    bool has_direct() const override { return true; }
+    int64_t init_mem(const int8_t* xs0) override {
+        dim3 g((unsigned)((sched->Mpad + 255) / 256), (unsigned)tiles), b(256);
+        k_tile_init_mem<T><<<g, b, 0, stream>>>(xs0, sched->d_perm.p, mem.p, sched->Mpad, tiles);
+        ODESAT_CUDA(cudaGetLastError());
+        return 1;
+    }
+    int64_t import_v(const T* v, int64_t Rp) override {
+        ODESAT_CUDA(cudaMemsetAsync(oor.p, 0, 4, stream));
+        dim3 g((unsigned)((f.N + 31) / 32), (unsigned)((tiles * W + 31) / 32)), b(32, 8);
+        k_tile_import_v<T><<<g, b, 0, stream>>>(v, Rp, R, f.N, vt.p, tiles, oor.p);
+        unsigned h = 0;
+        ODESAT_CUDA(cudaMemcpyAsync(&h, oor.p, 4, cudaMemcpyDeviceToHost, stream));
+        ODESAT_CUDA(cudaStreamSynchronize(stream));
+        ODESAT_CUDA(cudaGetLastError());
+        need_rterm = h != 0;
+        return 1;
+    }
+    int64_t verify_direct(uint32_t* bad) override {
+        if ((size_t)f.N > 48 * 1024) return 0;
+        k_tile_verify<T><<<(unsigned)tiles, 512, (size_t)f.N, stream>>>(vt.p, sched->d_entry.p, sched->d_perm.p, f.N, sched->Mpad, R, bad);
+        ODESAT_CUDA(cudaGetLastError());
+        return 1;
+    }
+    int64_t assignment_direct(int64_t r, uint8_t* out_dev) override {
+        k_tile_assignment<T><<<(unsigned)((f.N + 255) / 256), 256, 0, stream>>>(vt.p, f.N, r, out_dev);
         ODESAT_CUDA(cudaGetLastError());
         return 1;
     }
