@@ -436,7 +436,7 @@ int odesat_batch_info(const odesat_batch* b, int32_t* engine, int64_t* kernel_la
 int odesat_batch_init(odesat_batch* b, uint64_t seed, int64_t replica_offset) {
     return guarded([&] {
         ODESAT_REQUIRE(b != nullptr, "batch is NULL");
-        b->impl->upload(nullptr, nullptr, nullptr, true);   // reset flags / step / dt
+        b->impl->reset();                                    // flags / step / dt of a fresh batch
         b->impl->init(seed, replica_offset, true, true, true);
     });
 }
