@@ -110,9 +110,22 @@ template <typename T> struct BatchImpl final : BatchBase {
         dtv.alloc((size_t)std::max<int64_t>(Rp, 1), &dev_bytes);
         key.alloc(1, &dev_bytes);
         if (engine == ODESAT_ENGINE_TILE) {
-            if (use_ctile) tile.reset(new ClusterTileEngine<T>(*f, R, schedule, stream, &dev_bytes));
-            else tile.reset(new TileEngine<T>(*f, R, schedule, stream, &dev_bytes));
-        } else {
+            // supports() works from estimates; the compiled schedule can still turn out too large for shared memory.
+            // Under AUTO fall back one engine at a time instead of failing the call.
+            try {
+                if (use_ctile) tile.reset(new ClusterTileEngine<T>(*f, R, schedule, stream, &dev_bytes));
+                else tile.reset(new TileEngine<T>(*f, R, schedule, stream, &dev_bytes));
+            } catch (const Error& e) {
+                if (e.code != ODESAT_EUNSUPPORTED || engine_ != ODESAT_ENGINE_AUTO) throw;
+                tile.reset();
+                if (!use_ctile && c_auto) {
+                    try { tile.reset(new ClusterTileEngine<T>(*f, R, schedule, stream, &dev_bytes)); }
+                    catch (const Error& e2) { if (e2.code != ODESAT_EUNSUPPORTED) throw; tile.reset(); }
+                }
+                if (!tile) engine = ODESAT_ENGINE_GATHER;
+            }
+        }
+        if (engine != ODESAT_ENGINE_TILE) {
             S[0].alloc(N, M, Rp, &dev_bytes);   // S[1] (derivatives / adaptive ping-pong) on first use
             pick_slab();
             unsat.alloc((size_t)std::max<int64_t>(Rp, 1), &dev_bytes);

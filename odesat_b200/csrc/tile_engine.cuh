@@ -767,7 +767,10 @@ template <typename T> struct TileEngine final : TileBase<T> {
         if (f.K != 3) return no("needs uniform clause length 3");
         if (!f.distinct_vars) return no("a clause repeats a variable");
         if (f.N > 16383) return no("more than 16383 variables");
-        if (pick_depth(f.N, 128, 4096) < 2) return no("variables do not fit in 227 KB of shared memory");
+        // a 512-thread CTA with a ring of 2 and an item table sized for this formula must fit beside the rows
+        // (a narrower CTA would fit a few more variables but cannot hide the shared-memory latency: the
+        // one-replica kernel of tile_cluster.cuh takes over from there)
+        if (pick_depth(f.N, 512, (int)(f.M / 512 + 4 * f.max_degree + 64)) < 2) return no("variables do not fit in 227 KB of shared memory");
         return true;
     }
     static bool preferred(const odesat_formula&, int64_t R) { return R >= 8; }
