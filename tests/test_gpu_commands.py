@@ -40,3 +40,20 @@ def test_batch_and_inter_commands(golden_dir):
     # without -s `inter` is adaptive with ONE dt shared by the replicas (quirk Q7) — offered, sequential like the reference
     res = commands.inter(str(golden_dir / "aim100_sat.cnf"), 4, step_number=20000, seed=3, log=lambda s: None)
     assert res.is_satisfiable and res.winner >= 0
+
+
+def test_inter_driver_script_single_process():
+    """scripts/inter_multi_gpu.py (the torchrun program of SURVEY §8e) with one rank: early exit, winner
+    verified on device and host, and the same winner as the single-batch reference run (--check)."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, str(root / "scripts" / "inter_multi_gpu.py"), "--vars", "2000", "--alpha", "3.0",
+                        "--dt", "0.04", "--replicas", "64", "--max-steps", "6000", "--check"],
+                       capture_output=True, text=True, timeout=300, cwd=str(root))
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert d["winner"] >= 0 and d["winner_verified_sat"] is True and d["single_gpu_same_winner"] is True
+    assert d["flag_step"] < d["steps_run"] <= d["flag_step"] + d["chunk"]
