@@ -433,6 +433,188 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
     }
 }
 
+// ---- TMA-fed variant (ODESAT_TILE_TMA=1) -----------------------------------------------------------------------
+// Same algorithm as k_tile_fixed<…, ER = true>, but the ring is filled by the copy engine: after the barrier that
+// ends an item, ONE thread arms the stage's mbarrier with the byte count and issues two bulk copies
+// (cp.async.bulk, global → shared, complete_tx on the mbarrier) — the item's {xs, xl} cells (cnt·16 B) and its
+// packed clause words (cnt·8 B, rounded up to 16) — instead of every thread issuing its own LDGSTS.  Consumers
+// wait on the stage's mbarrier parity.  A stage is shared by the whole CTA, so every non-empty item ends with a
+// block barrier (with one item per level, as the schedules are cut, that is the level barrier anyway), and the
+// write-back of a cell is followed by fence.proxy.async.global so that a later bulk read of the same slots (next
+// step) sees it.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes) {
+    asm volatile("{\n.reg .b64 t;\nmbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1;\n}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
+    asm volatile(
+        "{\n.reg .pred P1;\nTMA_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra TMA_DONE;\nbra TMA_WAIT;\nTMA_DONE:\n}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <typename T, int NT, int D>
+__global__ void __launch_bounds__(NT, 1) k_tile_fixed_tma(const TileArgs<T> a) {
+    constexpr int W = TileTraits<T>::W;
+    using Row = typename TileTraits<T>::Row;
+    using Mem = typename TileTraits<T>::Mem;
+    using IO = RowIO<T, W>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Row* rows = reinterpret_cast<Row*>(smem_raw);
+    Mem* ring_m = reinterpret_cast<Mem*>(smem_raw + (size_t)a.N * sizeof(Row));
+    uint2* ring_e = reinterpret_cast<uint2*>(ring_m + D * NT);
+    uint2* s_items = reinterpret_cast<uint2*>(ring_e + D * NT);
+    const int n_items = a.n_items;                             // a multiple of D (host-checked)
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(s_items + n_items + 2);
+
+    const unsigned tid = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    T* vt = a.vt + tile * a.N * W;
+    Mem* tile_mem = a.mem + tile * a.Mpad;
+    const uint2* entries = reinterpret_cast<const uint2*>(a.entry);
+
+    for (int i = tid; i < n_items; i += NT) {
+        const uint32_t it = a.items[i];
+        s_items[i] = make_uint2(it & 0xFFFFFu, ((it >> 20) & 0x7FFu) | (it & TILE_ITEM_LAST));
+    }
+    for (int i = tid; i < a.N; i += NT) {
+        T v[W], dv[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) { v[w] = vt[(int64_t)i * W + w]; dv[w] = T(0); }
+        rows[i] = IO::pack(v, dv);
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) mbar_init(bars + k, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    bool valid[W], frozen[W];
+    int32_t solved_at[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        valid[w] = tile * W + w < a.R;
+        solved_at[w] = valid[w] ? a.solved[tile * W + w] : 0;
+        frozen[w] = !valid[w] || (a.freeze && solved_at[w] >= 0);
+    }
+    __syncthreads();
+    auto refill = [&](int k, uint2 it) {   // thread 0 only; stage k is free
+        const unsigned cnt = it.y & 0x7FFFFFFFu;
+        if (cnt == 0) return;
+        const unsigned bm = cnt * (unsigned)sizeof(Mem), be = ((cnt + 1u) & ~1u) * 8u;
+        mbar_expect_tx(bars + k, bm + be);
+        bulk_g2s(ring_m + k * NT, tile_mem + it.x, bm, bars + k);
+        bulk_g2s(ring_e + k * NT, entries + it.x, be, bars + k);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) refill(k, s_items[k]);
+    }
+    unsigned parity = 0;   // bit k: phase the consumers of stage k wait for next
+
+    for (int s = 0; s < a.nsteps; ++s) {
+        bool all_frozen = true;
+#pragma unroll
+        for (int w = 0; w < W; ++w) all_frozen = all_frozen && frozen[w];
+        if (all_frozen) break;
+        bool unsat[W];
+        float mx[2] = {0.0f, 0.0f};
+        T dtw[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) { unsat[w] = false; dtw[w] = frozen[w] ? T(0) : a.dt; }
+        for (int base = 0; base < n_items; base += D) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                const int i = base + k;
+                const uint2 it = s_items[i];
+                const unsigned cnt = it.y & 0x7FFFFFFFu;     // block-uniform
+                if (cnt != 0) {
+                    mbar_wait(bars + k, (parity >> k) & 1u);
+                    parity ^= 1u << k;
+                    if (tid < cnt) {
+                        const Mem mm = ring_m[k * NT + tid];
+                        const uint2 e = ring_e[k * NT + tid];
+                        Row* const r0 = reinterpret_cast<Row*>(smem_raw + (e.x & 0x3FFF0u));
+                        Row* const r1 = reinterpret_cast<Row*>(smem_raw + ((e.x >> 14) & 0x3FFF0u));
+                        Row* const r2 = reinterpret_cast<Row*>(smem_raw + (e.y & 0x3FFF0u));
+                        const T q[3] = {(e.y >> 24) & 1u ? T(-1) : T(1), (e.y >> 25) & 1u ? T(-1) : T(1), (e.y >> 26) & 1u ? T(-1) : T(1)};
+                        T v[3][W], d[3][W], xs[W], xl[W];
+                        IO::unpack(*r0, v[0], d[0]);
+                        IO::unpack(*r1, v[1], d[1]);
+                        IO::unpack(*r2, v[2], d[2]);
+                        IO::unpack_mem(mm, xs, xl);
+                        if constexpr (W == 2 && sizeof(T) == 4) {
+                            const float2 v2[3] = {make_float2(v[0][0], v[0][1]), make_float2(v[1][0], v[1][1]), make_float2(v[2][0], v[2][1])};
+                            float2 d2[3] = {make_float2(d[0][0], d[0][1]), make_float2(d[1][0], d[1][1]), make_float2(d[2][0], d[2][1])};
+                            float2 xs2 = make_float2(xs[0], xs[1]), xl2 = make_float2(xl[0], xl[1]);
+                            clause_math_f32x2(v2, d2, q, xs2, xl2, mx, make_float2(dtw[0], dtw[1]), a.xl_max);
+#pragma unroll
+                            for (int j = 0; j < 3; ++j) { d[j][0] = d2[j].x; d[j][1] = d2[j].y; }
+                            xs[0] = xs2.x; xs[1] = xs2.y; xl[0] = xl2.x; xl[1] = xl2.y;
+                        } else {
+#pragma unroll
+                            for (int w = 0; w < W; ++w) {
+                                const T vv[3] = {v[0][w], v[1][w], v[2][w]};
+                                T dd[3] = {d[0][w], d[1][w], d[2][w]};
+                                clause_math<T, false>(vv, dd, q, xs[w], xl[w], frozen[w], unsat[w], dtw[w], a.zeta, a.xl_max);
+                                d[0][w] = dd[0]; d[1][w] = dd[1]; d[2][w] = dd[2];
+                            }
+                        }
+                        IO::store_dv(r0, d[0]);
+                        IO::store_dv(r1, d[1]);
+                        IO::store_dv(r2, d[2]);
+                        __stcg(tile_mem + it.x + tid, IO::pack_mem(xs, xl));
+                        asm volatile("fence.proxy.async.global;" ::: "memory");   // a later bulk read of this slot must see the store
+                    }
+                    __syncthreads();                         // the stage is consumed and the level's dv stores are complete
+                }
+                if (tid == 0) {                              // also after an empty item: its stage feeds item i + D
+                    int nx = i + D;
+                    if (nx >= n_items) nx -= n_items;
+                    refill(k, s_items[nx]);
+                }
+            }
+        }
+        if constexpr (W == 2 && sizeof(T) == 4) { unsat[0] = !(mx[0] < 0.5f); unsat[1] = !(mx[1] < 0.5f); }
+        unsigned any_unsat = 0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) any_unsat |= (__syncthreads_or((int)unsat[w]) ? 1u : 0u) << w;
+        for (int i = tid; i < a.N; i += NT) {
+            T v[W], dv[W];
+            IO::unpack(rows[i], v, dv);
+#pragma unroll
+            for (int w = 0; w < W; ++w) { v[w] = euler_clamp(v[w], dv[w], dtw[w], T(-1), T(1)); dv[w] = T(0); }
+            rows[i] = IO::pack(v, dv);
+        }
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            if (valid[w] && !frozen[w] && !((any_unsat >> w) & 1u)) {
+                if (solved_at[w] < 0) {
+                    solved_at[w] = a.step0 + s;
+                    if (tid == 0) a.solved[tile * W + w] = solved_at[w];
+                }
+                if (a.freeze) frozen[w] = true;
+            }
+        }
+        __syncthreads();
+    }
+    // drain the copies that were requested for a step that does not run
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+        if ((s_items[k].y & 0x7FFFFFFFu) != 0u) mbar_wait(bars + k, (parity >> k) & 1u);
+    for (int i = tid; i < a.N; i += NT) {
+        T v[W], dv[W];
+        IO::unpack(rows[i], v, dv);
+#pragma unroll
+        for (int w = 0; w < W; ++w) vt[(int64_t)i * W + w] = v[w];
+    }
+}
+
 // ---- small-instance persistent kernel ---------------------------------------------
 // When every level of the schedule fits in one warp (≤ 32 clauses, e.g. the reference's
 // aim-100 fixtures: N = 100, M = 160) a replica tile is integrated by ONE WARP with the whole
@@ -744,6 +926,12 @@ template <typename T> struct TileEngine final : TileBase<T> {
     DevBuf<Mem> mem;
     DevBuf<unsigned> oor;
     bool need_rterm = true;
+    // ring fed by cp.async.bulk (k_tile_fixed_tma).  Measured on B200 at the headline size, ms/step TMA vs per-thread
+    // cp.async: f32 BALANCED 768 threads 0.566 vs 0.589 (the default below); 640 threads 0.709 vs 0.596; EXACT 512
+    // threads 0.700 vs 0.636; f64 0.653 vs 0.629 — the elected-thread issue and the per-item barrier only pay where an
+    // item is a full 768-clause level.  ODESAT_TILE_TMA=0/1 overrides.
+    int tma_env = [] { const char* e = std::getenv("ODESAT_TILE_TMA"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
+    bool use_tma = false;
     bool small = false;   // one warp per tile, state resident in shared memory (k_tile_small)
     int nt = 512;
     int chunk = 64;   // Euler steps per launch
@@ -852,6 +1040,7 @@ template <typename T> struct TileEngine final : TileBase<T> {
         if (it == f.tile_sched.end()) it = f.tile_sched.emplace(key, build_tile_schedule(f, *lv, kind, nt, depth)).first;
         sched = it->second;
         if (smem_bytes(f.N, sched->n_items, nt, depth) > kMaxSmem) throw Error(ODESAT_EUNSUPPORTED, "schedule does not fit in shared memory");
+        use_tma = tma_env >= 0 ? tma_env == 1 : (sizeof(T) == 4 && kind == ODESAT_SCHED_BALANCED && nt == 768 && depth % 3 == 0);
         vt.alloc((size_t)(tiles * f.N * W), ledger);
         mem.alloc((size_t)(tiles * sched->Mpad), ledger);
         oor.alloc(1, ledger);
@@ -922,8 +1111,21 @@ template <typename T> struct TileEngine final : TileBase<T> {
         ensure_max_smem(k_tile_fixed<T, NT, D, STRICT, (NT < 1024)>, (int)kMaxSmem, attr_devs);
         k_tile_fixed<T, NT, D, STRICT, (NT < 1024)><<<(unsigned)tiles, NT, smem, stream>>>(a);
     }
+    template <int NT, int D> bool launch_tma(const TileArgs<T>& a) {
+        const size_t smem = (size_t)f.N * 16 + (size_t)NT * D * 24 + (size_t)(sched->n_items + 2) * 8 + (size_t)D * 8;
+        if (smem > kMaxSmem || sched->n_items % D != 0) return false;
+        static uint64_t attr_devs = 0;
+        ensure_max_smem(k_tile_fixed_tma<T, NT, D>, (int)kMaxSmem, attr_devs);
+        k_tile_fixed_tma<T, NT, D><<<(unsigned)tiles, NT, smem, stream>>>(a);
+        return true;
+    }
     template <int NT> void launch_d(const TileArgs<T>& a, bool strict) {
-        if (strict) { launch<NT, 2, true>(a); return; }   // ring of 2 divides every schedule padding
+        if (strict) { launch<NT, 2, true>(a); return; }
+        if (use_tma) {
+            if constexpr (NT == 768 || NT == 512 || NT == 640) {
+                if (depth % 3 == 0 ? launch_tma<NT, 3>(a) : launch_tma<NT, 2>(a)) return;
+            }
+        }   // ring of 2 divides every schedule padding
         switch (depth) {
             case 2: launch<NT, 2, false>(a); break;
             case 3: launch<NT, 3, false>(a); break;
