@@ -439,9 +439,9 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
 // (cp.async.bulk, global → shared, complete_tx on the mbarrier) — the item's {xs, xl} cells (cnt·16 B) and its
 // packed clause words (cnt·8 B, rounded up to 16) — instead of every thread issuing its own LDGSTS.  Consumers
 // wait on the stage's mbarrier parity.  A stage is shared by the whole CTA, so every non-empty item ends with a
-// block barrier (with one item per level, as the schedules are cut, that is the level barrier anyway), and the
-// write-back of a cell is followed by fence.proxy.async.global so that a later bulk read of the same slots (next
-// step) sees it.
+// block barrier (with one item per level, as the schedules are cut, that is the level barrier anyway), and every
+// thread issues fence.proxy.async.global once per item so that the bulk read of a slot in the NEXT step sees this
+// step's write-back (generic-proxy store → async-proxy read).
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(void* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -534,6 +534,10 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed_tma(const TileArgs<T> a) {
                 const uint2 it = s_items[i];
                 const unsigned cnt = it.y & 0x7FFFFFFFu;     // block-uniform
                 if (cnt != 0) {
+                    // Cross-proxy ordering for the write-backs: a slot written here is read again by a bulk copy almost a
+                    // whole step later; the fence is cumulative over this thread's earlier stores, so issuing it one item
+                    // late (when the previous item's store has long completed) covers them without stalling at the barrier.
+                    asm volatile("fence.proxy.async.global;" ::: "memory");
                     mbar_wait(bars + k, (parity >> k) & 1u);
                     parity ^= 1u << k;
                     if (tid < cnt) {
@@ -569,7 +573,6 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed_tma(const TileArgs<T> a) {
                         IO::store_dv(r1, d[1]);
                         IO::store_dv(r2, d[2]);
                         __stcg(tile_mem + it.x + tid, IO::pack_mem(xs, xl));
-                        asm volatile("fence.proxy.async.global;" ::: "memory");   // a later bulk read of this slot must see the store
                     }
                     __syncthreads();                         // the stage is consumed and the level's dv stores are complete
                 }
@@ -927,9 +930,9 @@ template <typename T> struct TileEngine final : TileBase<T> {
     DevBuf<unsigned> oor;
     bool need_rterm = true;
     // ring fed by cp.async.bulk (k_tile_fixed_tma).  Measured on B200 at the headline size, ms/step TMA vs per-thread
-    // cp.async: f32 BALANCED 768 threads 0.566 vs 0.589 (the default below); 640 threads 0.709 vs 0.596; EXACT 512
-    // threads 0.700 vs 0.636; f64 0.653 vs 0.629 — the elected-thread issue and the per-item barrier only pay where an
-    // item is a full 768-clause level.  ODESAT_TILE_TMA=0/1 overrides.
+    // cp.async: BALANCED 768 threads f32 0.553 vs 0.589, f64 0.600 vs 0.629 (at 640) — the defaults below; f32 640
+    // threads 0.592 vs 0.596; EXACT 512 threads 0.681 vs 0.636 — the elected-thread issue and the per-item barrier
+    // only pay where an item is a full 768-clause level.  ODESAT_TILE_TMA=0/1 overrides.
     int tma_env = [] { const char* e = std::getenv("ODESAT_TILE_TMA"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
     bool use_tma = false;
     bool small = false;   // one warp per tile, state resident in shared memory (k_tile_small)
@@ -1024,7 +1027,8 @@ template <typename T> struct TileEngine final : TileBase<T> {
                 for (const auto& b : l->bucket) items += (double)((b.size() + c - 1) / c);
                 // width preference measured on B200 at the headline size (BALANCED, ms/step at 512/640/768/1024 threads:
                 // f32 0.611/0.596/0.588/0.603, f64 0.656/0.637/0.659/0.666): the widest CTA is not the fastest
-                const double pref = c == 1024 ? (sizeof(T) == 4 ? 1.12 : 1.25) : (c == 768 && sizeof(T) == 8 ? 1.10 : 1.0);
+                // (with the TMA-fed ring, BALANCED f64 is fastest at 768 threads too: 0.600 ms against 0.629 at 640 with cp.async)
+                const double pref = c == 1024 ? (sizeof(T) == 4 ? 1.12 : 1.25) : (c == 768 && sizeof(T) == 8 && kind == ODESAT_SCHED_EXACT ? 1.10 : 1.0);
                 const double cost = items * (454.0 + c) * pref;
                 if (cost < best) { best = cost; nt = c; lv = l; }
             }
@@ -1040,7 +1044,7 @@ template <typename T> struct TileEngine final : TileBase<T> {
         if (it == f.tile_sched.end()) it = f.tile_sched.emplace(key, build_tile_schedule(f, *lv, kind, nt, depth)).first;
         sched = it->second;
         if (smem_bytes(f.N, sched->n_items, nt, depth) > kMaxSmem) throw Error(ODESAT_EUNSUPPORTED, "schedule does not fit in shared memory");
-        use_tma = tma_env >= 0 ? tma_env == 1 : (sizeof(T) == 4 && kind == ODESAT_SCHED_BALANCED && nt == 768 && depth % 3 == 0);
+        use_tma = tma_env >= 0 ? tma_env == 1 : (kind == ODESAT_SCHED_BALANCED && nt == 768 && depth % 3 == 0);
         vt.alloc((size_t)(tiles * f.N * W), ledger);
         mem.alloc((size_t)(tiles * sched->Mpad), ledger);
         oor.alloc(1, ledger);
