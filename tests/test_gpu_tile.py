@@ -184,3 +184,35 @@ def test_long_trajectory_stays_bit_identical(prec):
         assert eq(st, ost)
         assert eq(gv, v) and eq(gxs, xs) and eq(gxl, xl)
     assert (np.abs(v) == 1).mean() > 0.02                      # the run really touches the clamps
+
+
+@pytest.mark.parametrize("prec", [L.F32, L.F64])
+def test_tma_fed_kernel_equals_the_per_thread_ring_at_the_bench_configuration(monkeypatch, prec):
+    """BASELINE configs[2] shape, BALANCED schedule (the bench default): the kernel whose ring is fed by
+    cp.async.bulk + mbarriers (k_tile_fixed_tma, default at 768 threads) and the per-thread cp.async kernel walk
+    the same schedule, so 70 steps must agree BIT FOR BIT; and one step agrees with the oracle within the
+    north-star tolerance (the BALANCED order differs from the reference's only in the summation order of dv)."""
+    f = cnf.random_ksat(10_000, 4.3, seed=20240613)
+    D = S.DeviceFormula(f)
+    F = O.OracleFormula(f.varnum, f.clause_off, f.lits)
+    dtype = B.np_dtype(prec)
+    R = 96
+    v, xs, xl = F.init_batch(3, R, dtype)
+    out = {}
+    for tma in ("1", "0"):
+        monkeypatch.setenv("ODESAT_TILE_TMA", tma)
+        b = B.ReplicaBatch(D, R, prec, L.ENGINE_TILE, L.SCHED_BALANCED)
+        b.upload(v, xs, xl)
+        b.run_fixed(0.01, 0.001, 1, freeze=False)
+        first = b.download()
+        b.run_fixed(0.01, 0.001, 69, freeze=False)          # crosses the 64-step launch chunk
+        out[tma] = (first, b.download())
+        b.close()
+    for a, c in zip(out["1"][0] + out["1"][1], out["0"][0] + out["0"][1]):
+        assert eq(a, c)
+    o = [v.copy(), xs.copy(), xl.copy()]
+    F.batch_fixed(*o, 0.01, 0.001, 1, freeze=False, nthreads=O.host_cores())
+    g = out["1"][0]
+    tol = dict(rtol=1e-5, atol=1e-6) if prec == L.F32 else dict(rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(g[0], o[0], **tol)
+    assert eq(g[1], o[1]) and eq(g[2], o[2])
