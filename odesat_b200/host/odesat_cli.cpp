@@ -6,6 +6,7 @@
 // preprocess.hpp) and replays the elimination trace on the result (main.rs:186-187).  Not restated:
 // `stoch`.  Extra flags: --seed (the reference's RNG is OS-seeded), --f32.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -172,8 +173,10 @@ int main(int argc, char** argv) {
         std::vector<int64_t> solved((std::size_t)R);
         int64_t winner = -1, run = 0;
         // states are generated on the device (main.rs:283-289 with a seeded generator)
+        const auto t0 = std::chrono::steady_clock::now();
         system::check(odesat_simulate_batch(F.handle(), R, nullptr, nullptr, nullptr, seed, 0, &p, mode, 0, solved.data(),
                                             verified.data(), &winner, assignment.data(), &run));
+        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         std::map<std::size_t, bool> values;                              // cnf.rs:301-315
         for (const auto& kv : name_map) values[kv.first] = assignment[kv.second] != 0;
         if (cmd == "solve") {
@@ -184,6 +187,11 @@ int main(int argc, char** argv) {
         const bool ok = evaluate_cnf(values, raw);
         std::printf("%sChecking if solution vector satisfies formula: %s\n", cmd == "solve" ? "" : "\n", ok ? "true" : "false");
         std::fprintf(stderr, "[odesat_b200] replicas=%lld steps_run=%lld winner=%lld\n", (long long)R, (long long)run, (long long)winner);
+        // one JSON record of the integration (the driver reports throughput next to the reference's lines)
+        std::fprintf(stderr, "{\"variables\": %zu, \"clauses\": %zu, \"replicas\": %lld, \"steps_run\": %lld, \"seconds\": %.6f, "
+                             "\"clause_evals_per_s\": %.4g, \"precision\": \"%s\"}\n",
+                     f.varnum, f.clauses.size(), (long long)R, (long long)run, sec,
+                     sec > 0 ? (double)run * (double)f.clauses.size() * (double)R / sec : 0.0, f32 ? "f32" : "f64");
         std::printf("Rendering variable assignments...\n");
         std::string render;                                              // cnf.rs:289-298
         for (const auto& kv : values) render += std::to_string(kv.first) + " " + (kv.second ? "1" : "0") + "\n";
