@@ -16,8 +16,11 @@
  *    `odesat_last_error()` returns a thread-local message for the last non-zero status.
  *  - the reference's `Option<T>` arguments are passed as sentinels: NaN for floating-point
  *    options, a negative value for `Option<usize>`.
- *  - handles are not thread-safe; one handle drives the CUDA device that was current when it
- *    was created.  Calls are synchronous: results are on the host when they return.
+ *  - handles are not thread-safe.  A formula handle lives on the CUDA device that was current when it was
+ *    created; the replica-batch calls (odesat_simulate_batch*, odesat_simulate_inter) drive `params->n_gpus`
+ *    devices of the process from that one handle (contiguous replica shards, the formula replicated on each
+ *    device, one stream per shard, no data-path collective — see odesat_params::n_gpus).  Calls are
+ *    synchronous: results are on the host when they return.  The caller's current device is restored.
  *  - there is NO CPU fallback.  Without a CUDA device every compute entry point returns
  *    ODESAT_ECUDA.
  */
@@ -30,7 +33,7 @@
 extern "C" {
 #endif
 
-#define ODESAT_B200_ABI_VERSION 1
+#define ODESAT_B200_ABI_VERSION 2   /* 2: odesat_params gained n_gpus / sub_batches; async batch entry points */
 
 typedef enum odesat_status {
     ODESAT_OK = 0,
@@ -84,6 +87,16 @@ typedef struct odesat_params {
     int32_t schedule;    /* odesat_schedule                                                     */
     int32_t chunk;       /* Euler steps between early-exit polls; <= 0 → 32 (1024 on the persistent
                             small-instance kernel)                                               */
+    int32_t n_gpus;      /* replica batches only: CUDA devices to shard the replicas over (replica r of R goes
+                            to shard r·G/R, main.rs:278-308 / system.rs:279-289 have no cross-replica data flow);
+                            <= 0 → 1; more than odesat_device_count() → ODESAT_EINVAL.  The only exchange is
+                            the early-exit word: every shard posts (first flagged step << 32 | replica) and its
+                            count of unflagged replicas to pinned host memory after each chunk, the host takes
+                            the minimum one chunk late while the next chunk is already running, and that chunk's
+                            kernels read the previous key on the device and do nothing once it is set.        */
+    int32_t sub_batches; /* shards per device with their own stream, so that the host→device copy of one
+                            shard's initial state overlaps the integration of the previous one; <= 0 → auto
+                            (4 when v0 comes from the host and a device gets >= 2048 replicas, else 1)       */
 } odesat_params;
 
 typedef struct odesat_formula odesat_formula;   /* device-resident CSR + variable→clause transpose */
@@ -175,6 +188,11 @@ int odesat_simulate_f32(const odesat_formula* f, float* v, float* xs, float* xl,
  *                 system.rs:357)
  *  assignment   : [N] thresholded state of the winner
  *  steps_run    : outer Euler steps executed by the device loop
+ * INTER with fixed steps and write_back != 0 leaves EVERY replica after exactly steps_run steps, like the reference's
+ * lock-step loop (system.rs:279-293): a chunk that ran past the winning step is replayed from a device-side snapshot
+ * of the chunk's start.  Without write_back only the winner's state is defined (the others may be up to two chunks
+ * ahead), and solved_step reports flags up to the winning step only.
+ * R == 0: nothing runs; winner = -1, steps_run = 0, assignment zero-filled.
  * Adaptive INTER (params.step_size = NaN) runs the reference's loop literally: the replicas take their steps
  * one after the other inside an outer step and share ONE dt (system.rs:314), and the loop
  * stops right after the outer step in which the first replica flags — a sequential dependency replica →
@@ -234,6 +252,20 @@ int odesat_batch_status(odesat_batch* b, int64_t* solved_step, int64_t* steps_do
 /* min over replicas of (solved_step << 32 | replica) — the early-exit key the multi-GPU layer
  * all-reduces (MIN); INT64_MAX when no replica has flagged. */
 int odesat_batch_first_solved(odesat_batch* b, int64_t* key);
+/* ---- asynchronous pieces of the step loop (what odesat_simulate_batch is built from; they let a multi-process
+ *      host layer put its own collective — e.g. an NCCL MIN all-reduce of the key — on the batch's stream) ----
+ * The CUDA stream every kernel and copy of this batch is issued on (a cudaStream_t). */
+int odesat_batch_stream(const odesat_batch* b, void** stream);
+/* Enqueue n fixed Euler steps and return at once.  stop_key (may be NULL) is a DEVICE pointer to one uint64 early-exit
+ * key; when the launches start and find *stop_key != INT64_MAX they do nothing (a chunk issued speculatively after the
+ * chunk in which some replica, on any rank, flagged). */
+int odesat_batch_run_fixed_async(odesat_batch* b, double dt, double zeta, int64_t n, int32_t freeze,
+                                 const uint64_t* stop_key);
+/* Enqueue the reduction of the flags: key_out[0] = min over replicas of (solved_step << 32 | replica_offset + r)
+ * (INT64_MAX: none), key_out[1] = number of replicas not flagged yet.  key_out is a DEVICE pointer to two uint64. */
+int odesat_batch_post_key(odesat_batch* b, int64_t replica_offset, uint64_t* key_out);
+/* Wait for everything enqueued on the batch's stream. */
+int odesat_batch_sync(odesat_batch* b);
 /* cnf.rs:246-264 on the device: verified[r] = thresholded state of replica r satisfies the CNF. */
 int odesat_batch_verify(odesat_batch* b, uint8_t* verified);
 /* system.rs:238 for one replica: assignment[i] = v[i] > 0. */

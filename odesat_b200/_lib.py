@@ -31,17 +31,17 @@ class Params(C.Structure):
     """odesat_params (include/odesat_b200.h)."""
     _fields_ = [("tolerance", C.c_double), ("step_size", C.c_double), ("steps", C.c_int64),
                 ("learning_rate", C.c_double), ("precision", C.c_int32), ("engine", C.c_int32),
-                ("schedule", C.c_int32), ("chunk", C.c_int32)]
+                ("schedule", C.c_int32), ("chunk", C.c_int32), ("n_gpus", C.c_int32), ("sub_batches", C.c_int32)]
 
 
 def make_params(tolerance=None, step_size=None, steps=None, learning_rate=None, precision=F64,
-                engine=ENGINE_AUTO, schedule=SCHED_EXACT, chunk=0) -> Params:
+                engine=ENGINE_AUTO, schedule=SCHED_EXACT, chunk=0, n_gpus=1, sub_batches=0) -> Params:
     nan = float("nan")
     return Params(nan if tolerance is None else float(tolerance),
                   nan if step_size is None else float(step_size),
                   -1 if steps is None else int(steps),
                   nan if learning_rate is None else float(learning_rate),
-                  int(precision), int(engine), int(schedule), int(chunk))
+                  int(precision), int(engine), int(schedule), int(chunk), int(n_gpus), int(sub_batches))
 
 
 def build(force: bool = False) -> Path:
@@ -100,6 +100,10 @@ _SIGS = {
     "odesat_batch_download": [_P, _P, _P, _P],
     "odesat_batch_run_fixed": [_P, _D, _D, _I64, _I32, C.POINTER(C.c_float)],
     "odesat_batch_run_adaptive": [_P, _D, _D, _I64, C.POINTER(C.c_float)],
+    "odesat_batch_stream": [_P, C.POINTER(_P)],
+    "odesat_batch_run_fixed_async": [_P, _D, _D, _I64, _I32, _P],
+    "odesat_batch_post_key": [_P, _I64, _P],
+    "odesat_batch_sync": [_P],
     "odesat_batch_status": [_P, _P, _PI64],
     "odesat_batch_first_solved": [_P, _PI64],
     "odesat_batch_verify": [_P, _P],

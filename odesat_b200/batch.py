@@ -102,6 +102,26 @@ class ReplicaBatch:
         L.check(L.lib().odesat_batch_run_adaptive(self._h, tolerance, zeta, n, C.byref(ms) if timed else None))
         return ms.value if timed else None
 
+    # -- asynchronous pieces (multi-process host layer) --------------------------------------------
+    @property
+    def stream(self) -> int:
+        """cudaStream_t of the batch as an integer (wrap with torch.cuda.ExternalStream)."""
+        s = C.c_void_p()
+        L.check(L.lib().odesat_batch_stream(self._h, C.byref(s)))
+        return int(s.value or 0)
+
+    def run_fixed_async(self, dt: float, zeta: float, n: int, freeze: bool = True, stop_key_ptr: int = 0) -> None:
+        """Enqueue n fixed steps; `stop_key_ptr` is a DEVICE pointer to one int64 key (0: none)."""
+        L.check(L.lib().odesat_batch_run_fixed_async(self._h, dt, zeta, n, int(freeze),
+                                                     C.c_void_p(stop_key_ptr) if stop_key_ptr else None))
+
+    def post_key(self, replica_offset: int, key_out_ptr: int) -> None:
+        """Enqueue the flag reduction into two DEVICE int64 words {min key, unflagged replicas}."""
+        L.check(L.lib().odesat_batch_post_key(self._h, replica_offset, C.c_void_p(key_out_ptr)))
+
+    def sync(self) -> None:
+        L.check(L.lib().odesat_batch_sync(self._h))
+
     # -- results ---------------------------------------------------------------------------------
     def status(self) -> Tuple[np.ndarray, int]:
         s = np.empty(self.R, np.int64)
@@ -142,11 +162,13 @@ class BatchResult:
 def simulate_batch(formula: DeviceFormula, R: int, v=None, xs=None, xl=None, *, seed: int = 1,
                    replica_offset: int = 0, tolerance=None, step_size=None, steps=None, learning_rate=None,
                    precision: int = L.F32, engine: int = L.ENGINE_AUTO, schedule: int = L.SCHED_EXACT,
-                   chunk: int = 0, mode: int = L.MODE_BATCH, write_back: bool = False) -> BatchResult:
+                   chunk: int = 0, mode: int = L.MODE_BATCH, write_back: bool = False, n_gpus: int = 1,
+                   sub_batches: int = 0) -> BatchResult:
     """One call of `odesat_simulate_batch[_f32]`: HOST buffers in, results out (the e2e path).
     v/xs/xl: numpy arrays of shape [R][N]/[R][M]/[R][M] or raw host pointers (ints), or None to
-    generate on the device.  Host element type: float32 when precision is F32, else float64."""
-    p = L.make_params(tolerance, step_size, steps, learning_rate, precision, engine, schedule, chunk)
+    generate on the device.  Host element type: float32 when precision is F32, else float64.
+    n_gpus: devices of THIS process the library shards the replicas over (odesat_params::n_gpus)."""
+    p = L.make_params(tolerance, step_size, steps, learning_rate, precision, engine, schedule, chunk, n_gpus, sub_batches)
     fn = L.lib().odesat_simulate_batch_f32 if precision == L.F32 else L.lib().odesat_simulate_batch
 
     def ptr(a):
@@ -154,10 +176,10 @@ def simulate_batch(formula: DeviceFormula, R: int, v=None, xs=None, xl=None, *, 
             return None
         return _ptr(a) if isinstance(a, np.ndarray) else C.c_void_p(int(a))
 
-    solved = np.empty(R, np.int64)
-    ver = np.empty(R, np.uint8)
-    assign = np.empty(formula.varnum, np.uint8)
-    win, run = C.c_int64(), C.c_int64()
+    solved = np.full(R, -1, np.int64)
+    ver = np.zeros(R, np.uint8)
+    assign = np.zeros(formula.varnum, np.uint8)
+    win, run = C.c_int64(-1), C.c_int64(0)
     L.check(fn(formula.handle, R, ptr(v), ptr(xs), ptr(xl), seed, replica_offset, C.byref(p), mode, int(write_back),
                _ptr(solved), _ptr(ver), C.byref(win), _ptr(assign), C.byref(run)))
     return BatchResult(solved, ver, win.value, assign, run.value)
@@ -217,6 +239,9 @@ def run_sharded_inter(batch, dt: float, zeta: float, max_steps: int, chunk: int,
     single-process reference run inside an initialised group)."""
     done = 0
     key = NO_KEY
+    if max_steps == 0:
+        # system.rs:274, 353 (quirk Q8): `state_res` starts all-true, so with zero steps replica 0 is returned
+        return ShardedResult(NO_KEY, 0, 0, 0)
     while max_steps < 0 or done < max_steps:
         n = chunk if max_steps < 0 else min(chunk, max_steps - done)
         batch.run_fixed(dt, zeta, n, True)

@@ -23,16 +23,48 @@ struct BatchBase {
     int precision = ODESAT_F64, engine = ODESAT_ENGINE_GATHER, schedule = ODESAT_SCHED_EXACT;
     int64_t launches = 0, dev_bytes = 0;
     int64_t step = 0;   // Euler steps issued since init/upload
+    int device = 0;     // CUDA device that owns the buffers and the stream
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // Early-exit words, KEY_SLOTS slots of {min key, unflagged replicas}: device copy (read by the next chunk's
+    // kernels as their stop key), pinned host mirror (read by the polling host one chunk late), one event per slot.
+    static constexpr int KEY_SLOTS = 3;                  // 0/1: chunk parity of the step loop; 2: synchronous queries
+    unsigned long long* d_key = nullptr;
+    unsigned long long* h_key = nullptr;
+    cudaEvent_t ev_key[KEY_SLOTS] = {nullptr, nullptr, nullptr};
     virtual ~BatchBase() {
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        for (cudaEvent_t e : ev_key) if (e) cudaEventDestroy(e);
+        if (d_key) cudaFree(d_key);
+        if (h_key) cudaFreeHost(h_key);
         if (stream) cudaStreamDestroy(stream);
     }
+    void sync() {
+        ODESAT_CUDA(cudaStreamSynchronize(stream));
+        ODESAT_CUDA(cudaGetLastError());
+    }
+    const unsigned long long* key_dev(int slot) const { return d_key + 2 * slot; }
+    // enqueue: key / unflagged count of the current flags → device slot → pinned host slot; never blocks
+    virtual void post_key(int slot, int64_t replica_offset) = 0;
+    // the same reduction into caller-owned device words (no host mirror)
+    virtual void post_key_to(int64_t replica_offset, unsigned long long* out_dev) = 0;
+    // block until the slot's words are on the host
+    void wait_key(int slot, int64_t* key, int64_t* unflagged) {
+        ODESAT_CUDA(cudaEventSynchronize(ev_key[slot]));
+        if (key) *key = (int64_t)h_key[2 * slot];
+        if (unflagged) *unflagged = (int64_t)h_key[2 * slot + 1];
+    }
+    // step loop pieces that only ENQUEUE work (the synchronous run_* below add timing and a stream sync)
+    virtual void run_fixed_async(double dt, double zeta, int64_t n, int freeze, const unsigned long long* stop_key) = 0;
+    virtual void run_adaptive_async(double tol, double zeta, int64_t n) = 0;
+    // device-to-device copy of state + flags + step counter, and back (lock-step `inter`, see drive())
+    virtual void snapshot() = 0;
+    virtual void restore() = 0;
     virtual void reset() = 0;   // flags, step counter, dt back to the state of a fresh batch
     // finalize = false: an upload() of the remaining arrays follows immediately (saves one layout conversion)
     virtual void init(uint64_t seed, int64_t replica_offset, bool gen_v, bool gen_xs, bool gen_xl, bool finalize = true) = 0;
+    // enqueue only; the host buffers must stay valid until the next sync()
     virtual void upload(const void* v, const void* xs, const void* xl, bool reset) = 0;
     virtual void download(void* v, void* xs, void* xl) = 0;
     virtual void run_fixed(double dt, double zeta, int64_t n, int freeze, float* ms) = 0;
@@ -75,8 +107,11 @@ template <typename T> struct BatchImpl final : BatchBase {
     DevBuf<T> dtv;
     DevBuf<T> staging;
     DevBuf<uint8_t> small8;
-    DevBuf<unsigned long long> key;
     DevBuf<double> dscratch;
+    StateBuf<T> Snap;           // snapshot of the gather-engine state
+    DevBuf<int32_t> solved_snap;
+    int64_t step_snap = 0;
+    bool v_in_range_snap = false;
     // ---- tile engine state ----
     std::unique_ptr<TileBase<T>> tile;   // TileEngine (one CTA per tile) or ClusterTileEngine (one cluster per replica)
 
@@ -86,9 +121,14 @@ template <typename T> struct BatchImpl final : BatchBase {
         Rp = R >= 32 ? pad32(R) : R;
         precision = sizeof(T) == 4 ? ODESAT_F32 : ODESAT_F64;
         schedule = schedule_;
+        ODESAT_CUDA(cudaGetDevice(&device));
         ODESAT_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         ODESAT_CUDA(cudaEventCreate(&ev0));
         ODESAT_CUDA(cudaEventCreate(&ev1));
+        for (cudaEvent_t& e : ev_key) ODESAT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ODESAT_CUDA(cudaMalloc((void**)&d_key, 2 * KEY_SLOTS * sizeof(unsigned long long)));
+        ODESAT_CUDA(cudaHostAlloc((void**)&h_key, 2 * KEY_SLOTS * sizeof(unsigned long long), cudaHostAllocDefault));
+        dev_bytes += 2 * KEY_SLOTS * (int64_t)sizeof(unsigned long long);
         std::string why, why_c;
         const bool tile_ok = TileEngine<T>::supports(*f, R, &why);
         const bool ctile_ok = ClusterTileEngine<T>::supports(*f, R, &why_c);
@@ -108,7 +148,6 @@ template <typename T> struct BatchImpl final : BatchBase {
         const int64_t N = f->N, M = f->M;
         solved.alloc((size_t)std::max<int64_t>(Rp, 1), &dev_bytes);
         dtv.alloc((size_t)std::max<int64_t>(Rp, 1), &dev_bytes);
-        key.alloc(1, &dev_bytes);
         if (engine == ODESAT_ENGINE_TILE) {
             // supports() works from estimates; the compiled schedule can still turn out too large for shared memory.
             // Under AUTO fall back one engine at a time instead of failing the call.
@@ -149,9 +188,10 @@ template <typename T> struct BatchImpl final : BatchBase {
         ODESAT_CUDA(cudaMemsetAsync(solved.p, 0xFF, solved.bytes(), stream));   // -1
         if (unsat.p) ODESAT_CUDA(cudaMemsetAsync(unsat.p, 0, unsat.bytes(), stream));
         if (err.p) ODESAT_CUDA(cudaMemsetAsync(err.p, 0, err.bytes(), stream));
-        std::vector<T> h((size_t)std::max<int64_t>(Rp, 1), T(0.01));             // system.rs:205
-        ODESAT_CUDA(cudaMemcpyAsync(dtv.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
-        ODESAT_CUDA(cudaStreamSynchronize(stream));
+        {
+            const int64_t n = std::max<int64_t>(Rp, 1);
+            k_fill<T><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dtv.p, n, T(0.01));   // system.rs:205
+        }
         if (tile) tile->reset_control();
     }
 
@@ -229,7 +269,6 @@ template <typename T> struct BatchImpl final : BatchBase {
                 launches += tile->import_v(s.v.p, Rp);
             }
             canon_current = false;
-            ODESAT_CUDA(cudaStreamSynchronize(stream));
             ODESAT_CUDA(cudaGetLastError());
             return;
         }
@@ -247,7 +286,6 @@ template <typename T> struct BatchImpl final : BatchBase {
         if (gen_v) v_in_range = true;                    // v0 ∈ [-1, 1) by construction
         if (tile && !finalize) { canon_ahead = true; canon_current = false; return; }
         canon_to_tile();
-        ODESAT_CUDA(cudaStreamSynchronize(stream));
     }
 
     void upload(const void* v, const void* xs, const void* xl, bool reset) override {
@@ -257,7 +295,6 @@ template <typename T> struct BatchImpl final : BatchBase {
             put(v, s.v.p, f->N);
             launches += tile->import_v(s.v.p, Rp);
             canon_current = false;
-            ODESAT_CUDA(cudaStreamSynchronize(stream));
             ODESAT_CUDA(cudaGetLastError());
             return;
         }
@@ -267,8 +304,7 @@ template <typename T> struct BatchImpl final : BatchBase {
         if (xl) put(xl, s.xl.p, f->M);
         ODESAT_CUDA(cudaGetLastError());
         canon_to_tile();
-        ODESAT_CUDA(cudaStreamSynchronize(stream));
-        if (v && !tile) check_v_range();
+        if (!tile) check_range();
     }
 
     void download(void* v, void* xs, void* xl) override {
@@ -292,13 +328,14 @@ template <typename T> struct BatchImpl final : BatchBase {
     // [-1, 1] (true after any step: system.rs:96 clamps; checked on upload) and zeta is finite
     bool v_in_range = false;
     DevBuf<unsigned> range_flag;
-    void check_v_range() {
-        if (tile || R == 0 || f->N == 0) { v_in_range = true; return; }
+    // the fast arithmetic needs every v finite in [-1, 1] and every memory in mem_in_fast_domain (tile_engine.cuh)
+    void check_range() {
+        if (tile || R == 0 || f->N + f->M == 0) { v_in_range = true; return; }
         if (!range_flag.p) range_flag.alloc(1, &dev_bytes);
         ODESAT_CUDA(cudaMemsetAsync(range_flag.p, 0, 4, stream));
         dim3 g, b;
-        geom(f->N, g, b);
-        k_check_range<T><<<g, b, 0, stream>>>(S[cur].v.p, f->N, R, Rp, range_flag.p);
+        geom(f->N + f->M, g, b);
+        k_check_range<T><<<g, b, 0, stream>>>(S[cur].v.p, S[cur].xs.p, S[cur].xl.p, f->N, f->M, R, Rp, range_flag.p);
         ++launches;
         unsigned h = 1;
         ODESAT_CUDA(cudaMemcpyAsync(&h, range_flag.p, 4, cudaMemcpyDeviceToHost, stream));
@@ -401,8 +438,9 @@ template <typename T> struct BatchImpl final : BatchBase {
         ensure_max_smem(k_solve_small<T, NT>, (int)kSmallSmem, attr_devs);
         k_solve_small<T, NT><<<(unsigned)R, NT, smem, stream>>>(a);
     }
-    void run_small(bool adaptive, double dt, double tol, double zeta, int64_t n, int freeze) {
+    void run_small(bool adaptive, double dt, double tol, double zeta, int64_t n, int freeze, const unsigned long long* stop_key) {
         SmallArgs<T> a;
+        a.stop_key = stop_key;
         a.f = f->dev;
         a.R = R; a.Rp = Rp;
         a.v = S[cur].v.p; a.xs = S[cur].xs.p; a.xl = S[cur].xl.p;
@@ -436,25 +474,25 @@ template <typename T> struct BatchImpl final : BatchBase {
     }
 
     void run_fixed(double dt, double zeta, int64_t n, int freeze, float* ms) override {
+        time_begin(ms);
+        run_fixed_async(dt, zeta, n, freeze, nullptr);
+        time_end(ms);
+    }
+    void run_fixed_async(double dt, double zeta, int64_t n, int freeze, const unsigned long long* stop_key) override {
         ODESAT_REQUIRE(n >= 0, "negative step count");
         ODESAT_REQUIRE(step + n < (int64_t(1) << 31) - 4, "step counter overflow");
         if (tile) {
             if (canon_ahead) canon_to_tile();
-            time_begin(ms);
             if (n > 0) canon_current = false;
-            launches += tile->run_fixed((T)dt, (T)zeta, n, freeze, solved.p, step);
+            launches += tile->run_fixed((T)dt, (T)zeta, n, freeze, solved.p, step, stop_key);
             step += n;
-            time_end(ms);
             return;
         }
         if (small_ok(false)) {
-            time_begin(ms);
-            run_small(false, dt, 0.0, zeta, n, freeze);
+            run_small(false, dt, 0.0, zeta, n, freeze, stop_key);
             step += n;
-            time_end(ms);
             return;
         }
-        time_begin(ms);
         auto one_step = [&](int64_t r0, int64_t r1, int64_t at_step) {
             GatherArgs<T> a = base_args(zeta, true);   // in place: each element is read and written by its own thread
             a.rep0 = r0; a.rep1 = r1;
@@ -463,6 +501,7 @@ template <typename T> struct BatchImpl final : BatchBase {
             a.dt = (T)dt;
             a.step = (int32_t)at_step;
             a.freeze = freeze;
+            a.stop_key = stop_key;
             launch_gather<G_FIXED>(a);
             v_in_range = true;                           // every stepped v is clamped (system.rs:96); frozen replicas were clamped before
         };
@@ -476,23 +515,25 @@ template <typename T> struct BatchImpl final : BatchBase {
             for (int64_t i = 0; i < n; ++i) one_step(0, R, step + i);
         }
         step += n;
-        time_end(ms);
+        ODESAT_CUDA(cudaGetLastError());
     }
 
     void run_adaptive(double tol, double zeta, int64_t n, float* ms) override {
+        time_begin(ms);
+        run_adaptive_async(tol, zeta, n);
+        time_end(ms);
+    }
+    void run_adaptive_async(double tol, double zeta, int64_t n) override {
         ODESAT_REQUIRE(n >= 0, "negative step count");
         ODESAT_REQUIRE(step + n < (int64_t(1) << 31) - 4, "step counter overflow");
         if (tile) throw Error(ODESAT_EUNSUPPORTED, "the tile engine integrates fixed steps only; use the gather engine for adaptive steps");
         if (small_ok(true)) {
-            time_begin(ms);
-            run_small(true, 0.0, tol, zeta, n, 1);
+            run_small(true, 0.0, tol, zeta, n, 1, nullptr);
             step += n;
-            time_end(ms);
             return;
         }
         ensure_alt();
         if (!H.allocated()) { H.alloc(f->N, f->M, Rp, &dev_bytes); Fb.alloc(f->N, f->M, Rp, &dev_bytes); }
-        time_begin(ms);
         for (int64_t i = 0; i < n; ++i) {
             GatherArgs<T> a = base_args(zeta);
             a.dt_arr = dtv.p;
@@ -516,7 +557,38 @@ template <typename T> struct BatchImpl final : BatchBase {
             ++step;
             v_in_range = true;   // stepped replicas are clamped; flagged ones are never evaluated again
         }
-        time_end(ms);
+        ODESAT_CUDA(cudaGetLastError());
+    }
+
+    // ---- snapshot / restore (lock-step `inter`) --------------------------------------------------
+    void snapshot() override {
+        if (!solved_snap.p) solved_snap.alloc(solved.n, &dev_bytes);
+        ODESAT_CUDA(cudaMemcpyAsync(solved_snap.p, solved.p, solved.bytes(), cudaMemcpyDeviceToDevice, stream));
+        step_snap = step;
+        v_in_range_snap = v_in_range;
+        if (tile) {
+            if (canon_ahead) canon_to_tile();
+            tile->snapshot();
+            return;
+        }
+        if (!Snap.allocated()) Snap.alloc(f->N, f->M, Rp, &dev_bytes);
+        ODESAT_CUDA(cudaMemcpyAsync(Snap.v.p, S[cur].v.p, S[cur].v.bytes(), cudaMemcpyDeviceToDevice, stream));
+        ODESAT_CUDA(cudaMemcpyAsync(Snap.xs.p, S[cur].xs.p, S[cur].xs.bytes(), cudaMemcpyDeviceToDevice, stream));
+        ODESAT_CUDA(cudaMemcpyAsync(Snap.xl.p, S[cur].xl.p, S[cur].xl.bytes(), cudaMemcpyDeviceToDevice, stream));
+    }
+    void restore() override {
+        ODESAT_REQUIRE(solved_snap.p != nullptr, "restore without a snapshot");
+        ODESAT_CUDA(cudaMemcpyAsync(solved.p, solved_snap.p, solved.bytes(), cudaMemcpyDeviceToDevice, stream));
+        step = step_snap;
+        v_in_range = v_in_range_snap;
+        if (tile) {
+            tile->restore();
+            canon_current = false;
+            return;
+        }
+        ODESAT_CUDA(cudaMemcpyAsync(S[cur].v.p, Snap.v.p, S[cur].v.bytes(), cudaMemcpyDeviceToDevice, stream));
+        ODESAT_CUDA(cudaMemcpyAsync(S[cur].xs.p, Snap.xs.p, S[cur].xs.bytes(), cudaMemcpyDeviceToDevice, stream));
+        ODESAT_CUDA(cudaMemcpyAsync(S[cur].xl.p, Snap.xl.p, S[cur].xl.bytes(), cudaMemcpyDeviceToDevice, stream));
     }
 
     int64_t run_inter_adaptive(double tol, double zeta, int64_t max_steps) override {
@@ -607,17 +679,22 @@ template <typename T> struct BatchImpl final : BatchBase {
         if (steps) *steps = step;
     }
 
+    void post_key(int slot, int64_t replica_offset) override {
+        k_first_key<<<1, 1024, 0, stream>>>(solved.p, R, replica_offset, d_key + 2 * slot);
+        ++launches;
+        ODESAT_CUDA(cudaMemcpyAsync(h_key + 2 * slot, d_key + 2 * slot, 16, cudaMemcpyDeviceToHost, stream));
+        ODESAT_CUDA(cudaEventRecord(ev_key[slot], stream));
+    }
+    void post_key_to(int64_t replica_offset, unsigned long long* out_dev) override {
+        k_first_key<<<1, 1024, 0, stream>>>(solved.p, R, replica_offset, out_dev);
+        ++launches;
+        ODESAT_CUDA(cudaGetLastError());
+    }
     int64_t first_key() override {
-        const unsigned long long init = (unsigned long long)std::numeric_limits<int64_t>::max();
-        ODESAT_CUDA(cudaMemcpyAsync(key.p, &init, 8, cudaMemcpyHostToDevice, stream));
-        if (R > 0) {
-            k_first_key<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(solved.p, R, 0, key.p);
-            ++launches;
-        }
-        unsigned long long h = 0;
-        ODESAT_CUDA(cudaMemcpyAsync(&h, key.p, 8, cudaMemcpyDeviceToHost, stream));
-        ODESAT_CUDA(cudaStreamSynchronize(stream));
-        return (int64_t)h;
+        post_key(2, 0);
+        int64_t k = 0;
+        wait_key(2, &k, nullptr);
+        return k;
     }
 
     void verify(uint8_t* out) override {

@@ -33,6 +33,15 @@ template <typename T> __device__ __forceinline__ T euler_clamp(T y, T dy, T dt, 
     return rmin(rmax(y + dt * dy, lo), hi);
 }
 
+// Memories on which the fast arithmetic is bit-identical to the literal statements: finite, and zero or of a
+// magnitude that keeps 0.5·xl·xs and its products with the clause minima normal (no underflow, no overflow).
+// Every memory the integrator itself produces qualifies (xs ∈ [ε, 1−ε] or ±1, xl ∈ [1, 1e4·M]); a caller-uploaded
+// inf / NaN / denormal sends the first step through the STRICT kernel.
+template <typename T> __device__ __forceinline__ bool mem_in_fast_domain(T x) {
+    const T a = fabs(x);
+    return a == T(0) || (a >= T(1e-12) && a <= T(1e12));   // false for NaN and inf
+}
+
 // Device view of a formula: clause CSR + variable→clause transpose.
 struct FormulaDev {
     int64_t N = 0, M = 0, L = 0;

@@ -7,6 +7,8 @@
 #pragma once
 #include <map>
 #include <memory>
+#include <string>
+#include <vector>
 
 #include "common.cuh"
 #include "host_util.hpp"
@@ -35,11 +37,30 @@ struct odesat_formula {
     // schedules keyed by kind * 4096 + warps per CTA
     mutable std::map<int, std::shared_ptr<odesat::TileLevels>> tile_levels;
     mutable std::map<int, std::shared_ptr<odesat::TileSchedule>> tile_sched;
-    // device buffers of the last odesat_simulate* call, reused by the next call of the same shape
-    // (allocating and freeing several GB per call costs more than the upload)
-    mutable std::shared_ptr<void> batch_cache;
-    mutable int64_t cache_R = -1;
-    mutable int cache_precision = -1, cache_engine = -1, cache_schedule = -1;
+    // copies of this formula on the other CUDA devices of the process (multi-GPU calls), built on first use
+    mutable std::map<int, std::unique_ptr<odesat_formula>> peers;
+    // device buffers of the last odesat_simulate* call — one batch per (device, sub-batch) shard — reused by the
+    // next call of the same shape (allocating and freeing several GB per call costs more than the upload).
+    // Declared after `peers`: the batches are destroyed before the formulas they point to.
+    mutable std::vector<std::shared_ptr<void>> batch_cache;
+    mutable std::string cache_key;
+
+    // this formula on CUDA device `dev_id` (the handle itself on its own device)
+    const odesat_formula* on_device(int dev_id) const {
+        if (dev_id == device) return this;
+        auto it = peers.find(dev_id);
+        if (it == peers.end()) {
+            std::unique_ptr<odesat_formula> c(new odesat_formula);
+            c->build(N, M, h_off.data(), h_lits.data());
+            int prev = 0;
+            ODESAT_CUDA(cudaGetDevice(&prev));
+            ODESAT_CUDA(cudaSetDevice(dev_id));
+            try { c->upload(); } catch (...) { cudaSetDevice(prev); throw; }
+            ODESAT_CUDA(cudaSetDevice(prev));
+            it = peers.emplace(dev_id, std::move(c)).first;
+        }
+        return it->second.get();
+    }
 
     double default_zeta() const {   // system.rs:164-173
         const double d = double(M) / double(N);

@@ -46,7 +46,15 @@ template <typename T> struct GatherArgs {
     typename ErrBits<T>::U* err = nullptr;   // [Rp] (B)
     int32_t step = 0;
     int32_t freeze = 0;
+    // `inter` early exit without a host round trip: the (all-reduced) key of the previous chunk of steps; when it
+    // names a flagged replica, the speculatively issued launches of this chunk do nothing
+    const unsigned long long* stop_key = nullptr;
 };
+
+constexpr unsigned long long GATHER_KEY_NONE = 0x7FFFFFFFFFFFFFFFull;
+template <typename T> __device__ __forceinline__ bool gather_stopped(const GatherArgs<T>& a) {
+    return a.stop_key != nullptr && *a.stop_key != GATHER_KEY_NONE;
+}
 
 template <typename T> __device__ __forceinline__ void err_max(typename ErrBits<T>::U* slot, T e) {
     if (e == e) {   // NaN-ignoring, like the reference's folds (system.rs:103)
@@ -232,6 +240,7 @@ __device__ __forceinline__ void clause_row(const GatherArgs<T>& a, int64_t m, in
 
 template <typename T, int K, int MODE, int V>
 __global__ void __launch_bounds__(256) k_clause_phase(const GatherArgs<T> a) {
+    if (gather_stopped(a)) return;
     const int64_t rep = a.rep0 + ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * V;
     if (rep >= a.rep1) return;
 #pragma unroll 2
@@ -244,12 +253,19 @@ __global__ void __launch_bounds__(256) k_clause_phase(const GatherArgs<T> a) {
 __device__ __forceinline__ float gfma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 __device__ __forceinline__ double gfma(double a, double b, double c) { return __fma_rn(a, b, c); }
 
-// any |v| > 1 or NaN in the batch? (decides whether the first step may use the fast arithmetic)
-template <typename T> __global__ void k_check_range(const T* v, int64_t N, int64_t R, int64_t Rp, unsigned* flag) {
+// any |v| > 1 or NaN, or a memory outside mem_in_fast_domain, in the batch?  (decides whether the first step may use
+// the fast arithmetic)
+template <typename T>
+__global__ void k_check_range(const T* v, const T* xs, const T* xl, int64_t N, int64_t M, int64_t R, int64_t Rp, unsigned* flag) {
     const int64_t rep = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
     const int64_t row = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
-    if (rep >= R || row >= N) return;
-    if (!(fabs(v[row * Rp + rep]) <= T(1))) *flag = 1u;
+    if (rep >= R || row >= N + M) return;
+    if (row < N) {
+        if (!(fabs(v[row * Rp + rep]) <= T(1))) *flag = 1u;
+    } else {
+        const int64_t m = row - N;
+        if (!mem_in_fast_domain(xs[m * Rp + rep]) || !mem_in_fast_domain(xl[m * Rp + rep])) *flag = 1u;
+    }
 }
 
 // ---- streaming clause phase (uniform 3-literal clauses) -------------------------------------------
@@ -295,6 +311,7 @@ __device__ __forceinline__ void cp_async_wait_dyn(int n) {   // wait until at mo
 template <typename T, int MODE, int V, int RPT>
 __global__ void __launch_bounds__(256) k_clause_stream(const GatherArgs<T> a) {
     static_assert(RPT >= 1 && RPT <= 4, "cp_async_wait_dyn covers up to 4 groups");
+    if (gather_stopped(a)) return;
     constexpr int CB = V * (int)sizeof(T);                       // bytes of one cell (V replicas of one row)
     extern __shared__ __align__(16) unsigned char stream_smem[];
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -563,6 +580,7 @@ __device__ __forceinline__ void var_row(const GatherArgs<T>& a, int64_t row, int
 
 template <typename T, int MODE, int V>
 __global__ void __launch_bounds__(256) k_var_phase(const GatherArgs<T> a) {
+    if (gather_stopped(a)) return;
     const int64_t rep = a.rep0 + ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * V;
     if (rep >= a.rep1) return;
     const int64_t rows = a.f.N > 0 ? a.f.N : 1;
@@ -673,13 +691,50 @@ __global__ void k_assignment(const T* v, int64_t N, int64_t Rp, int64_t rep, uin
     if (i < N) out[i] = v[i * Rp + rep] > T(0) ? 1 : 0;
 }
 
-// min over replicas of (solved_step << 32 | global replica index); INT64_MAX when none.
-__global__ void k_first_key(const int32_t* solved_step, int64_t R, int64_t replica_offset,
-                            unsigned long long* key) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R) return;
-    const int s = solved_step[r];
-    if (s >= 0) atomicMin(key, ((unsigned long long)s << 32) | (unsigned long long)(replica_offset + r));
+// min over replicas of (solved_step << 32 | global replica index), INT64_MAX when none, and the number of replicas
+// that have not flagged — ONE block, plain stores (no reset launch): out[0] = key, out[1] = unflagged count.
+// The early-exit word of `inter` / the all-done test of `batch`; 8 + 8 bytes per chunk of steps.
+__global__ void __launch_bounds__(1024) k_first_key(const int32_t* solved_step, int64_t R, int64_t replica_offset,
+                                                    unsigned long long* out) {
+    __shared__ unsigned long long s_key[32];
+    __shared__ unsigned s_cnt[32];
+    unsigned long long key = 0x7FFFFFFFFFFFFFFFull;
+    unsigned cnt = 0;
+    for (int64_t r = threadIdx.x; r < R; r += blockDim.x) {
+        const int s = solved_step[r];
+        if (s >= 0) {
+            const unsigned long long k = ((unsigned long long)s << 32) | (unsigned long long)(replica_offset + r);
+            key = k < key ? k : key;
+        } else {
+            ++cnt;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long k2 = __shfl_xor_sync(0xFFFFFFFFu, key, o);
+        key = k2 < key ? k2 : key;
+        cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s_key[threadIdx.x >> 5] = key; s_cnt[threadIdx.x >> 5] = cnt; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int nw = (blockDim.x + 31) >> 5;
+        key = (int)threadIdx.x < nw ? s_key[threadIdx.x] : 0x7FFFFFFFFFFFFFFFull;
+        cnt = (int)threadIdx.x < nw ? s_cnt[threadIdx.x] : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long k2 = __shfl_xor_sync(0xFFFFFFFFu, key, o);
+            key = k2 < key ? k2 : key;
+            cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+        }
+        if (threadIdx.x == 0) { out[0] = key; out[1] = cnt; }
+    }
+}
+
+// dt of every replica back to the initial step size (system.rs:205) without a host buffer
+template <typename T> __global__ void k_fill(T* p, int64_t n, T x) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = x;
 }
 
 // Host layout [R][X] (one vector per replica, the reference's Vec<State>) ↔ replica-major [X][Rp].

@@ -21,6 +21,7 @@ template <typename T> struct SmallArgs {
     int32_t* solved_step = nullptr;                   // [R] first flagged step, -1 = none
     T dt = T(0), tol = T(0), zeta = T(0), xl_max = T(0);
     int32_t step0 = 0, nsteps = 0, freeze = 0, adaptive = 0;
+    const unsigned long long* stop_key = nullptr;   // see GatherArgs
 };
 
 // elements of T the kernel keeps in shared memory
@@ -181,6 +182,7 @@ __device__ __forceinline__ void small_store(const SmallArgs<T>& a, const SmallSm
 // `simulate` / `batch`: one CTA per replica, the whole chunk of steps with the replica resident.
 template <typename T, int NT>
 __global__ void __launch_bounds__(NT) k_solve_small(const SmallArgs<T> a) {
+    if (a.stop_key != nullptr && *a.stop_key != 0x7FFFFFFFFFFFFFFFull) return;
     extern __shared__ __align__(16) unsigned char small_smem[];
     const SmallSmem<T> sm(small_smem, (int)a.f.N, (int)a.f.M, (int)a.f.L, a.adaptive != 0);
     const int64_t rep = blockIdx.x;

@@ -4,7 +4,9 @@
 // There is no CPU fallback in this file: every compute entry point needs a CUDA device.
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <limits>
+#include <string>
 #include <vector>
 
 #include "batch.cuh"
@@ -22,6 +24,19 @@ void require_device() {
     }
 }
 
+// RAII: makes `dev` current, restores the previous device on scope exit
+struct DeviceGuard {
+    int prev = 0;
+    explicit DeviceGuard(int dev) {
+        ODESAT_CUDA(cudaGetDevice(&prev));
+        if (dev != prev) ODESAT_CUDA(cudaSetDevice(dev));
+    }
+    ~DeviceGuard() { cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+// A batch on the device that is current (must be the formula's own device).
 BatchBase* make_batch(const odesat_formula* f, int64_t R, int precision, int engine, int schedule) {
     ODESAT_REQUIRE(f != nullptr, "formula is NULL");
     ODESAT_REQUIRE(R >= 0, "negative replica count");
@@ -36,21 +51,52 @@ BatchBase* make_batch(const odesat_formula* f, int64_t R, int precision, int eng
     return new BatchImpl<double>(f, R, engine, schedule);
 }
 
-// Batch whose device buffers live on the formula handle and are reused by the next
-// odesat_simulate* call of the same shape.
-BatchBase* cached_batch(const odesat_formula* f, int64_t R, int precision, int engine, int schedule) {
-    ODESAT_REQUIRE(f != nullptr, "formula is NULL");
-    if (f->batch_cache && f->cache_R == R && f->cache_precision == precision && f->cache_engine == engine &&
-        f->cache_schedule == schedule) {
-        BatchBase* b = static_cast<BatchBase*>(f->batch_cache.get());
-        b->reset();
-        return b;
+// One shard of a replica-batch call: replicas [off, off + R) of the call on one device, with its own stream.
+struct Shard {
+    BatchBase* b = nullptr;
+    int dev = 0;
+    int64_t off = 0, R = 0;
+};
+
+// Contiguous replica ranges: device g of G owns [g·R/G, (g+1)·R/G); a device's range is cut the
+// same way into `sub` sub-batches.  Devices: the formula's own first, then the others in ascending order.
+std::vector<Shard> plan_shards(const odesat_formula* f, int64_t R, int n_gpus, int sub) {
+    std::vector<int> devs{f->device};
+    for (int d = 0; (int)devs.size() < n_gpus; ++d) if (d != f->device) devs.push_back(d);
+    std::vector<Shard> out;
+    for (int g = 0; g < n_gpus; ++g) {
+        const int64_t lo = R * g / n_gpus, hi = R * (g + 1) / n_gpus;
+        for (int k = 0; k < sub; ++k) {
+            Shard s;
+            s.dev = devs[g];
+            s.off = lo + (hi - lo) * k / sub;
+            s.R = lo + (hi - lo) * (k + 1) / sub - s.off;
+            if (s.R > 0 || (g == 0 && k == 0)) out.push_back(s);   // an empty call keeps one (empty) shard
+        }
     }
-    f->batch_cache.reset();   // free the old buffers before allocating the new ones
-    BatchBase* b = make_batch(f, R, precision, engine, schedule);
-    f->batch_cache = std::shared_ptr<void>(b, [](void* p) { delete static_cast<BatchBase*>(p); });
-    f->cache_R = R; f->cache_precision = precision; f->cache_engine = engine; f->cache_schedule = schedule;
-    return b;
+    return out;
+}
+
+// Batches whose device buffers live on the formula handle and are reused by the next odesat_simulate* call of
+// the same shape.
+void cached_shards(const odesat_formula* f, std::vector<Shard>& sh, int precision, int engine, int schedule) {
+    std::string key = std::to_string(precision) + "/" + std::to_string(engine) + "/" + std::to_string(schedule);
+    for (const Shard& s : sh) key += "|" + std::to_string(s.dev) + ":" + std::to_string(s.off) + "+" + std::to_string(s.R);
+    if (f->cache_key != key || f->batch_cache.size() != sh.size()) {
+        f->batch_cache.clear();   // free the old buffers before allocating the new ones
+        f->cache_key.clear();
+        for (Shard& s : sh) {
+            DeviceGuard g(s.dev);
+            BatchBase* b = make_batch(f->on_device(s.dev), s.R, precision, engine, schedule);
+            f->batch_cache.emplace_back(std::shared_ptr<void>(b, [](void* p) { delete static_cast<BatchBase*>(p); }));
+        }
+        f->cache_key = key;
+    }
+    for (size_t i = 0; i < sh.size(); ++i) {
+        sh[i].b = static_cast<BatchBase*>(f->batch_cache[i].get());
+        DeviceGuard g(sh[i].dev);
+        sh[i].b->reset();
+    }
 }
 
 // Host buffers of type TH feeding a device batch of precision `prec`.
@@ -81,11 +127,14 @@ template <typename TH> struct HostIO {
     }
 };
 
+// Enqueues the upload; returns without waiting when the host type is the device precision (the caller's buffers
+// stay valid until the call's final sync), after a sync when a converted temporary was used.
 template <typename TH>
 void upload_host(BatchBase& b, const TH* v, const TH* xs, const TH* xl, bool reset) {
     HostIO<TH> io(b.precision);
     const size_t nv = (size_t)(b.R * b.f->N), nm = (size_t)(b.R * b.f->M);
     b.upload(io.in(0, v, nv), io.in(1, xs, nm), io.in(2, xl, nm), reset);
+    if (!io.same()) b.sync();
 }
 template <typename TH> void download_host(BatchBase& b, TH* v, TH* xs, TH* xl) {
     HostIO<TH> io(b.precision);
@@ -117,33 +166,99 @@ Resolved resolve(const odesat_formula* f, const odesat_params* p) {
     return r;
 }
 
-// The step loop of simulate / batch / simulate_inter with chunked early-exit polling.
-// BATCH stops when every replica has flagged; INTER when any has.  Returns the INTER key
-// (INT64_MAX when no replica flagged).
-int64_t drive(BatchBase& b, const Resolved& r, int mode, std::vector<int64_t>& solved) {
-    const int64_t NONE = std::numeric_limits<int64_t>::max();
-    solved.assign((size_t)b.R, -1);
-    int64_t key = NONE;
-    if (b.R == 0) return key;
-    int64_t done_steps = 0;
-    while (r.steps < 0 || done_steps < r.steps) {
-        const int64_t n = r.steps < 0 ? r.chunk : std::min<int64_t>(r.chunk, r.steps - done_steps);
-        if (r.fixed) b.run_fixed(r.dt, r.zeta, n, /*freeze=*/1, nullptr);
-        else b.run_adaptive(r.tol, r.zeta, n, nullptr);
-        done_steps += n;
-        if (mode == ODESAT_MODE_INTER) {
-            key = b.first_key();
-            if (key != NONE) break;
-        } else {
-            b.status(solved.data(), nullptr);
-            bool all = true;
-            for (int64_t x : solved) all = all && x >= 0;
-            if (all) break;
+constexpr int64_t NO_KEY = std::numeric_limits<int64_t>::max();
+
+struct DriveResult {
+    int64_t key = NO_KEY;   // INTER: min over all replicas of (first flagged step << 32 | replica index in the call)
+    int64_t run = 0;        // Euler steps of the loop up to and including the chunk that ended it
+};
+
+// The step loop of simulate / batch / simulate_inter over the shards of one call.
+//
+// Chunks of r.chunk steps are ENQUEUED on every shard's stream, each followed by the reduction of the shard's flags
+// into a pinned host slot (BatchBase::post_key); the host reads the slots of chunk c only after it has issued chunk
+// c + 1, so no stream ever drains while the host decides.  BATCH ends when no replica is left unflagged, INTER when
+// some replica has flagged.  The speculatively issued chunk is harmless: flagged replicas are frozen (freeze = 1),
+// and INTER kernels read the previous chunk's key on the device and do nothing once it is set.
+//
+// lockstep (INTER with fixed steps whose states are written back): the reference leaves EVERY replica after exactly
+// the winning step (system.rs:279-293), so a chunk is polled synchronously and, when it contains the winning step
+// s*, replayed from a snapshot of its start for exactly s* − start + 1 steps without freezing.
+//
+// `prepare(k)` enqueues shard k's inputs; it is called right before the shard's first chunk, so the host→device
+// copy of shard k + 1 overlaps the integration of shard k.
+template <typename Prepare>
+DriveResult drive(std::vector<Shard>& sh, const Resolved& r, int mode, bool lockstep, Prepare&& prepare) {
+    DriveResult out;
+    const bool inter = mode == ODESAT_MODE_INTER;
+    bool prepared = false;
+    int64_t total = 0;
+    for (const Shard& s : sh) total += s.R;
+    auto poll = [&](int slot, int64_t end_steps) {
+        int64_t key = NO_KEY, unflagged = 0;
+        for (Shard& s : sh) {
+            int64_t k = NO_KEY, u = 0;
+            DeviceGuard g(s.dev);
+            s.b->wait_key(slot, &k, &u);
+            key = std::min(key, k);
+            unflagged += u;
         }
+        if (inter ? key != NO_KEY : unflagged == 0) {
+            out.key = key;
+            out.run = end_steps;
+            return true;
+        }
+        out.key = key;
+        return false;
+    };
+    int64_t issued = 0, last_chunk = -1;
+    bool stopped = false;
+    if (total > 0) {
+        for (int64_t c = 0; r.steps < 0 || issued < r.steps; ++c) {
+            last_chunk = c;
+            const int64_t n = r.steps < 0 ? r.chunk : std::min<int64_t>(r.chunk, r.steps - issued);
+            const int slot = lockstep ? 0 : (int)(c & 1);
+            for (size_t k = 0; k < sh.size(); ++k) {
+                Shard& s = sh[k];
+                DeviceGuard g(s.dev);
+                if (c == 0) prepare(k);
+                if (lockstep && n > 1) s.b->snapshot();
+                const unsigned long long* stop = (inter && !lockstep && c > 0) ? s.b->key_dev((int)((c - 1) & 1)) : nullptr;
+                if (r.fixed) s.b->run_fixed_async(r.dt, r.zeta, n, /*freeze=*/1, stop);
+                else s.b->run_adaptive_async(r.tol, r.zeta, n);
+                s.b->post_key(slot, s.off);
+            }
+            prepared = true;
+            issued += n;
+            if (lockstep) {
+                if (poll(0, issued)) {
+                    const int64_t s_star = out.key >> 32;
+                    if (n > 1) {   // replay the chunk up to and including the winning step, nobody frozen
+                        const int64_t need = s_star - (issued - n) + 1;
+                        for (Shard& s : sh) {
+                            DeviceGuard g(s.dev);
+                            s.b->restore();
+                            s.b->run_fixed_async(r.dt, r.zeta, need, /*freeze=*/0, nullptr);
+                            s.b->post_key(0, s.off);
+                        }
+                        poll(0, issued);
+                    }
+                    out.run = s_star + 1;
+                    stopped = true;
+                    break;
+                }
+            } else if (c >= 1 && poll((int)((c - 1) & 1), issued - n)) {
+                stopped = true;
+                break;
+            }
+        }
+        if (!stopped && !lockstep && last_chunk >= 0) stopped = poll((int)(last_chunk & 1), issued);
+        if (!stopped) out.run = issued;
+        if (inter && out.key != NO_KEY) out.run = (out.key >> 32) + 1;
     }
-    b.status(solved.data(), nullptr);
-    if (mode == ODESAT_MODE_INTER && key == NONE) key = b.first_key();
-    return key;
+    if (!prepared) for (size_t k = 0; k < sh.size(); ++k) { DeviceGuard g(sh[k].dev); prepare(k); }
+    for (Shard& s : sh) { DeviceGuard g(s.dev); s.b->sync(); }
+    return out;
 }
 
 template <typename TH>
@@ -152,16 +267,28 @@ void simulate_impl(const odesat_formula* f, TH* v, TH* xs, TH* xl, const odesat_
     ODESAT_REQUIRE(f && v && xs && xl, "NULL state or formula");
     Resolved r = resolve(f, p);
     const int eng = (!r.fixed && p->engine == ODESAT_ENGINE_AUTO) ? ODESAT_ENGINE_GATHER : p->engine;
+    DeviceGuard guard(f->device);
     std::unique_ptr<BatchBase> b(make_batch(f, 1, p->precision, eng, p->schedule));
     if (p->chunk <= 0) r.chunk = b->preferred_chunk();
-    upload_host<TH>(*b, v, xs, xl, true);
-    std::vector<int64_t> solved;
-    drive(*b, r, ODESAT_MODE_BATCH, solved);
+    std::vector<Shard> sh(1);
+    sh[0].b = b.get(); sh[0].dev = f->device; sh[0].off = 0; sh[0].R = 1;
+    drive(sh, r, ODESAT_MODE_BATCH, false, [&](size_t) { upload_host<TH>(*b, v, xs, xl, true); });
+    int64_t solved = -1;
+    b->status(&solved, nullptr);
     download_host<TH>(*b, v, xs, xl);
     if (assignment) b->assignment(0, assignment);                                // system.rs:238
-    if (steps_taken) *steps_taken = solved[0] >= 0 ? solved[0] + 1 : (r.steps < 0 ? b->step : r.steps);
-    if (allsat) *allsat = solved[0] >= 0 ? 1 : 0;
+    if (steps_taken) *steps_taken = solved >= 0 ? solved + 1 : (r.steps < 0 ? b->step : r.steps);
+    if (allsat) *allsat = solved >= 0 ? 1 : 0;
     if (final_dt) { double d = r.dt; if (!r.fixed) b->get_dt(&d); *final_dt = d; }
+}
+
+int resolve_gpus(const odesat_params* p) {
+    const int want = p->n_gpus > 0 ? p->n_gpus : 1;
+    int have = 0;
+    if (cudaGetDeviceCount(&have) != cudaSuccess) { cudaGetLastError(); have = 0; }
+    if (have <= 0) throw Error(ODESAT_ECUDA, "no CUDA device available (odesat_b200 has no CPU fallback)");
+    ODESAT_REQUIRE(want <= have, "params.n_gpus exceeds the number of visible CUDA devices");
+    return want;
 }
 
 template <typename TH>
@@ -170,46 +297,83 @@ void simulate_batch_impl(const odesat_formula* f, int64_t R, TH* v, TH* xs, TH* 
                          int64_t* solved_step, uint8_t* verified, int64_t* winner, uint8_t* assignment,
                          int64_t* steps_run) {
     ODESAT_REQUIRE(f != nullptr, "formula is NULL");
+    ODESAT_REQUIRE(R >= 0, "negative replica count");
     ODESAT_REQUIRE(mode == ODESAT_MODE_BATCH || mode == ODESAT_MODE_INTER, "unknown mode");
     Resolved r = resolve(f, p);
     if (mode == ODESAT_MODE_BATCH) ODESAT_REQUIRE(r.steps >= 0, "batch needs a step count (main.rs:96-97)");
+    int G = resolve_gpus(p);
+    if (R == 0) {   // nothing to integrate (the reference's `batch` loop does not run; `inter` would index states[0])
+        if (winner) *winner = -1;
+        if (steps_run) *steps_run = 0;
+        if (assignment) std::memset(assignment, 0, (size_t)f->N);
+        return;
+    }
     // the tile engine integrates fixed steps only: adaptive runs resolve AUTO to the gather engine
     const int eng = (!r.fixed && p->engine == ODESAT_ENGINE_AUTO) ? ODESAT_ENGINE_GATHER : p->engine;
-    BatchBase* b = cached_batch(f, R, p->precision, eng, p->schedule);
-    if (p->chunk <= 0) r.chunk = b->preferred_chunk();
-    const int64_t NONE = std::numeric_limits<int64_t>::max();
+    const bool inter_adaptive = mode == ODESAT_MODE_INTER && !r.fixed;   // one dt shared by all replicas: sequential (Q7)
+    if (inter_adaptive) G = 1;
+    G = (int)std::min<int64_t>(G, R);
+    int sub = p->sub_batches;
+    if (const char* e = std::getenv("ODESAT_SUB_BATCHES")) sub = std::atoi(e);
+    if (sub <= 0) sub = (v != nullptr && r.fixed && R / G >= 2048) ? 4 : 1;
+    if (inter_adaptive) sub = 1;
+    sub = (int)std::max<int64_t>(1, std::min<int64_t>(sub, R / G));
+    std::vector<Shard> sh = plan_shards(f, R, G, sub);
+    cached_shards(f, sh, p->precision, eng, p->schedule);
+    if (p->chunk <= 0) r.chunk = sh[0].b->preferred_chunk();
+    const int64_t N = f->N, M = f->M;
     // main.rs:283-289: whatever the caller does not supply is generated on the device
-    if (!(v && xs && xl)) b->init(seed, replica_offset, !v, !xs, !xl, /*finalize=*/!(v || xs || xl));
-    if (v || xs || xl) upload_host<TH>(*b, v, xs, xl, (v && xs && xl));
-    std::vector<int64_t> solved;
-    int64_t key;
-    if (mode == ODESAT_MODE_INTER && !r.fixed) {
+    auto prepare = [&](size_t k) {
+        Shard& s = sh[k];
+        if (!(v && xs && xl)) s.b->init(seed, replica_offset + s.off, !v, !xs, !xl, /*finalize=*/!(v || xs || xl));
+        if (v || xs || xl)
+            upload_host<TH>(*s.b, v ? v + s.off * N : nullptr, xs ? xs + s.off * M : nullptr, xl ? xl + s.off * M : nullptr,
+                            /*reset=*/false);
+    };
+    std::vector<int64_t> solved((size_t)R, -1);
+    DriveResult dr;
+    if (inter_adaptive) {
         // adaptive inter: the replicas share ONE dt and step one after the other (system.rs:312-349, quirk Q7)
-        b->run_inter_adaptive(r.tol, r.zeta, r.steps);
-        solved.assign((size_t)R, -1);
-        b->status(solved.data(), nullptr);
-        key = b->first_key();
+        DeviceGuard g(sh[0].dev);
+        prepare(0);
+        sh[0].b->run_inter_adaptive(r.tol, r.zeta, r.steps);
+        dr.key = sh[0].b->first_key();
+        dr.run = sh[0].b->step;
+        if (dr.key != NO_KEY) dr.run = (dr.key >> 32) + 1;
     } else {
-        key = drive(*b, r, mode, solved);
+        const bool lockstep = mode == ODESAT_MODE_INTER && write_back != 0 && r.fixed;
+        dr = drive(sh, r, mode, lockstep, prepare);
     }
-    std::vector<uint8_t> ver((size_t)std::max<int64_t>(R, 1), 0);
-    b->verify(ver.data());                                                       // cnf.rs:246-264
+    std::vector<uint8_t> ver((size_t)R, 0);
+    for (Shard& s : sh) {
+        DeviceGuard g(s.dev);
+        s.b->status(solved.data() + s.off, nullptr);
+        s.b->verify(ver.data() + s.off);                                         // cnf.rs:246-264
+    }
     int64_t win = -1, src = 0;
-    int64_t run = b->step;
     if (mode == ODESAT_MODE_BATCH) {
         for (int64_t q = 0; q < R; ++q) if (ver[q]) { win = q; break; }          // main.rs:305-307
         src = win >= 0 ? win : R - 1;
     } else {
-        if (r.steps == 0) win = R > 0 ? 0 : -1;                                  // system.rs:274, 353 (Q8)
-        else if (key != NONE) { win = key & 0xFFFFFFFFll; run = (key >> 32) + 1; }
+        if (r.steps == 0) win = 0;                                               // system.rs:274, 353 (Q8)
+        else if (dr.key != NO_KEY) win = dr.key & 0xFFFFFFFFll;
         src = win >= 0 ? win : 0;                                                // system.rs:357
+        // flags raised after the winning step belong to steps the reference never runs
+        if (dr.key != NO_KEY) for (int64_t q = 0; q < R; ++q) if (solved[q] > (dr.key >> 32)) solved[q] = -1;
     }
     if (solved_step) for (int64_t q = 0; q < R; ++q) solved_step[q] = solved[q];
     if (verified) for (int64_t q = 0; q < R; ++q) verified[q] = ver[q];
     if (winner) *winner = win;
-    if (assignment && R > 0) b->assignment(src, assignment);
-    if (steps_run) *steps_run = run;
-    if (write_back) download_host<TH>(*b, v, xs, xl);
+    if (assignment) {
+        for (Shard& s : sh)
+            if (src >= s.off && src < s.off + s.R) { DeviceGuard g(s.dev); s.b->assignment(src - s.off, assignment); }
+    }
+    if (steps_run) *steps_run = dr.run;
+    if (write_back)
+        for (Shard& s : sh) {
+            DeviceGuard g(s.dev);
+            download_host<TH>(*s.b, v ? v + s.off * N : nullptr, xs ? xs + s.off * M : nullptr, xl ? xl + s.off * M : nullptr);
+        }
 }
 
 template <typename TH> std::unique_ptr<BatchBase> single(const odesat_formula* f, const TH* v, const TH* xs, const TH* xl) {
@@ -420,6 +584,8 @@ int odesat_batch_create(const odesat_formula* f, int64_t R, int32_t precision, i
         ODESAT_REQUIRE(out != nullptr, "out is NULL");
         *out = nullptr;
         std::unique_ptr<odesat_batch> b(new odesat_batch);
+        ODESAT_REQUIRE(f != nullptr, "formula is NULL");
+        DeviceGuard g(f->device);
         b->impl.reset(make_batch(f, R, precision, engine, schedule));
         *out = b.release();
     });
@@ -436,61 +602,100 @@ int odesat_batch_info(const odesat_batch* b, int32_t* engine, int64_t* kernel_la
 int odesat_batch_init(odesat_batch* b, uint64_t seed, int64_t replica_offset) {
     return guarded([&] {
         ODESAT_REQUIRE(b != nullptr, "batch is NULL");
+        DeviceGuard g(b->impl->device);
         b->impl->reset();                                    // flags / step / dt of a fresh batch
         b->impl->init(seed, replica_offset, true, true, true);
+        b->impl->sync();
     });
 }
 int odesat_batch_upload(odesat_batch* b, const void* v, const void* xs, const void* xl) {
     return guarded([&] {
         ODESAT_REQUIRE(b && v && xs && xl, "NULL argument");
+        DeviceGuard g(b->impl->device);
         b->impl->upload(v, xs, xl, true);
+        b->impl->sync();
     });
 }
 int odesat_batch_download(odesat_batch* b, void* v, void* xs, void* xl) {
     return guarded([&] {
         ODESAT_REQUIRE(b != nullptr, "batch is NULL");
+        DeviceGuard g(b->impl->device);
         b->impl->download(v, xs, xl);
     });
 }
 int odesat_batch_run_fixed(odesat_batch* b, double dt, double zeta, int64_t n, int32_t freeze, float* device_ms) {
     return guarded([&] {
         ODESAT_REQUIRE(b != nullptr, "batch is NULL");
+        DeviceGuard g(b->impl->device);
         b->impl->run_fixed(dt, zeta, n, freeze, device_ms);
     });
 }
 int odesat_batch_run_adaptive(odesat_batch* b, double tolerance, double zeta, int64_t n, float* device_ms) {
     return guarded([&] {
         ODESAT_REQUIRE(b != nullptr, "batch is NULL");
+        DeviceGuard g(b->impl->device);
         b->impl->run_adaptive(tolerance, zeta, n, device_ms);
+    });
+}
+int odesat_batch_stream(const odesat_batch* b, void** stream) {
+    return guarded([&] {
+        ODESAT_REQUIRE(b && stream, "NULL argument");
+        *stream = (void*)b->impl->stream;
+    });
+}
+int odesat_batch_run_fixed_async(odesat_batch* b, double dt, double zeta, int64_t n, int32_t freeze, const uint64_t* stop_key) {
+    return guarded([&] {
+        ODESAT_REQUIRE(b != nullptr, "batch is NULL");
+        DeviceGuard g(b->impl->device);
+        b->impl->run_fixed_async(dt, zeta, n, freeze, reinterpret_cast<const unsigned long long*>(stop_key));
+    });
+}
+int odesat_batch_post_key(odesat_batch* b, int64_t replica_offset, uint64_t* key_out) {
+    return guarded([&] {
+        ODESAT_REQUIRE(b && key_out, "NULL argument");
+        DeviceGuard g(b->impl->device);
+        b->impl->post_key_to(replica_offset, reinterpret_cast<unsigned long long*>(key_out));
+    });
+}
+int odesat_batch_sync(odesat_batch* b) {
+    return guarded([&] {
+        ODESAT_REQUIRE(b != nullptr, "batch is NULL");
+        DeviceGuard g(b->impl->device);
+        b->impl->sync();
     });
 }
 int odesat_batch_status(odesat_batch* b, int64_t* solved_step, int64_t* steps_done) {
     return guarded([&] {
         ODESAT_REQUIRE(b != nullptr, "batch is NULL");
+        DeviceGuard g(b->impl->device);
         b->impl->status(solved_step, steps_done);
     });
 }
 int odesat_batch_first_solved(odesat_batch* b, int64_t* key) {
     return guarded([&] {
         ODESAT_REQUIRE(b && key, "NULL argument");
+        DeviceGuard g(b->impl->device);
         *key = b->impl->first_key();
     });
 }
 int odesat_batch_verify(odesat_batch* b, uint8_t* verified) {
     return guarded([&] {
         ODESAT_REQUIRE(b && verified, "NULL argument");
+        DeviceGuard g(b->impl->device);
         b->impl->verify(verified);
     });
 }
 int odesat_batch_assignment(odesat_batch* b, int64_t replica, uint8_t* assignment) {
     return guarded([&] {
         ODESAT_REQUIRE(b && assignment, "NULL argument");
+        DeviceGuard g(b->impl->device);
         b->impl->assignment(replica, assignment);
     });
 }
 int odesat_batch_dt(odesat_batch* b, double* dt) {
     return guarded([&] {
         ODESAT_REQUIRE(b && dt, "NULL argument");
+        DeviceGuard g(b->impl->device);
         b->impl->get_dt(dt);
     });
 }

@@ -35,6 +35,8 @@ template <typename T> struct CTileArgs {
     int32_t* solved = nullptr;
     T dt = T(0), zeta = T(0), xl_max = T(0);
     int32_t step0 = 0, nsteps = 0, freeze = 0;
+    const unsigned long long* stop_key = nullptr;   // see TileArgs
+    const unsigned* oor = nullptr;                  // see TileArgs
 };
 
 // ---- distributed shared memory primitives -------------------------------------------------------
@@ -88,6 +90,8 @@ __global__ void __launch_bounds__(NT, 1) k_ctile_fixed(const CTileArgs<T> a) {
     uint2* s_items = reinterpret_cast<uint2*>(ring + D * NT);
     volatile unsigned* s_flags = reinterpret_cast<volatile unsigned*>(s_items + n_items);
 
+    const int s_first = launch_first_step<STRICT>(a);           // grid-uniform (same words for every CTA)
+    if (s_first >= a.nsteps) return;
     const unsigned tid = threadIdx.x;
     const unsigned rank = CL > 1 ? cluster_ctarank() : 0u;
     const int64_t rep = blockIdx.x / CL;                         // one replica per cluster
@@ -121,7 +125,7 @@ __global__ void __launch_bounds__(NT, 1) k_ctile_fixed(const CTileArgs<T> a) {
     uint2 e_next = make_uint2(0u, 0u);
     if (lane_slot < (it_next.y & 0x7FFFFFFFu)) e_next = __ldg(my_entry + it_next.x);
 
-    for (int s = 0; s < a.nsteps; ++s) {
+    for (int s = s_first; s < a.nsteps; ++s) {
         if (frozen) break;                                       // cluster-uniform: derived from the shared flags
         bool unsat = false;
         bool pending = false;                                    // arrived at a level barrier, not yet waited
@@ -258,6 +262,7 @@ __global__ void k_ctile_import(const T* __restrict__ v, const T* __restrict__ xs
         typename Pair2<T>::type p;
         p.x = m >= 0 ? xs[(int64_t)m * Rp + rep] : T(0);
         p.y = m >= 0 ? xl[(int64_t)m * Rp + rep] : T(0);
+        if (!mem_in_fast_domain(p.x) || !mem_in_fast_domain(p.y)) *out_of_range = 1u;
         mem[rep * Mpad + slot] = p;
     }
 }
@@ -288,10 +293,11 @@ template <typename T> struct ClusterTileEngine final : TileBase<T> {
     int64_t R;
     std::shared_ptr<TileSchedule> sched;
     cudaStream_t stream;
-    DevBuf<T> vt;
-    DevBuf<Pair> mem;
+    DevBuf<T> vt, vt_snap;
+    DevBuf<Pair> mem, mem_snap;
     DevBuf<unsigned> oor;
-    bool need_rterm = true;
+    bool need_rterm = true, oor_valid = false;   // see TileEngine
+    int64_t* ledger_ = nullptr;
     int cl = 1, nt = 1024, depth = 2, chunk = 64;
 
     static size_t smem_bytes(int64_t N, int n_items, int cl, int nt, int depth) {
@@ -329,7 +335,7 @@ template <typename T> struct ClusterTileEngine final : TileBase<T> {
         return true;
     }
 
-    ClusterTileEngine(const odesat_formula& f_, int64_t R_, int kind, cudaStream_t st, int64_t* ledger) : f(f_), R(R_), stream(st) {
+    ClusterTileEngine(const odesat_formula& f_, int64_t R_, int kind, cudaStream_t st, int64_t* ledger) : f(f_), R(R_), stream(st), ledger_(ledger) {
         if (const char* e = std::getenv("ODESAT_TILE_CHUNK")) { const int v = std::atoi(e); if (v > 0) chunk = v; }
         const int force_cl = forced_cluster();
         int want_nt = 0, want_d = 0;
@@ -369,7 +375,17 @@ template <typename T> struct ClusterTileEngine final : TileBase<T> {
         mem.alloc((size_t)(R * sched->Mpad), ledger);
         oor.alloc(1, ledger);
     }
-    void reset_control() override { need_rterm = true; }
+    void reset_control() override { need_rterm = true; oor_valid = false; }
+    void snapshot() override {
+        if (!vt_snap.p) { vt_snap.alloc(vt.n, ledger_); mem_snap.alloc(mem.n, ledger_); }
+        ODESAT_CUDA(cudaMemcpyAsync(vt_snap.p, vt.p, vt.bytes(), cudaMemcpyDeviceToDevice, stream));
+        ODESAT_CUDA(cudaMemcpyAsync(mem_snap.p, mem.p, mem.bytes(), cudaMemcpyDeviceToDevice, stream));
+    }
+    void restore() override {
+        ODESAT_REQUIRE(vt_snap.p != nullptr, "restore without a snapshot");
+        ODESAT_CUDA(cudaMemcpyAsync(vt.p, vt_snap.p, vt.bytes(), cudaMemcpyDeviceToDevice, stream));
+        ODESAT_CUDA(cudaMemcpyAsync(mem.p, mem_snap.p, mem.bytes(), cudaMemcpyDeviceToDevice, stream));
+    }
 
     void geom(int64_t rows, dim3& grid, dim3& block) const {
         int bx = 1;
@@ -383,11 +399,9 @@ template <typename T> struct ClusterTileEngine final : TileBase<T> {
         dim3 g, b;
         geom(f.N + sched->Mpad, g, b);
         k_ctile_import<T><<<g, b, 0, stream>>>(v, xs, xl, Rp, R, f.N, sched->Mpad, sched->d_perm.p, vt.p, mem.p, oor.p);
-        unsigned h = 0;
-        ODESAT_CUDA(cudaMemcpyAsync(&h, oor.p, 4, cudaMemcpyDeviceToHost, stream));
-        ODESAT_CUDA(cudaStreamSynchronize(stream));
         ODESAT_CUDA(cudaGetLastError());
-        need_rterm = h != 0;
+        need_rterm = true;
+        oor_valid = true;
         return 1;
     }
     int64_t export_state(T* v, T* xs, T* xl, int64_t Rp) override {
@@ -431,9 +445,15 @@ template <typename T> struct ClusterTileEngine final : TileBase<T> {
         else launch_d<NT, 4>(a, strict);
     }
 
-    int64_t run_fixed(T dt, T zeta, int64_t n, int freeze, int32_t* solved, int64_t step0) override {
+    int64_t run_fixed(T dt, T zeta, int64_t n, int freeze, int32_t* solved, int64_t step0,
+                      const unsigned long long* stop_key = nullptr) override {
         int64_t launches = 0;
         const bool zeta_ok = std::isfinite((double)zeta);
+        auto go = [&](const CTileArgs<T>& a, bool strict) {
+            if (nt == 512) launch_c<512>(a, strict);
+            else launch_c<1024>(a, strict);
+            ++launches;
+        };
         for (int64_t done = 0; done < n;) {
             const int64_t k = std::min<int64_t>(chunk, n - done);
             CTileArgs<T> a;
@@ -442,13 +462,25 @@ template <typename T> struct ClusterTileEngine final : TileBase<T> {
             a.vt = vt.p; a.mem = mem.p; a.solved = solved;
             a.dt = dt; a.zeta = zeta; a.xl_max = T(1e4) * T(f.M);
             a.step0 = (int32_t)(step0 + done); a.nsteps = (int32_t)k; a.freeze = freeze;
-            const bool strict = need_rterm || !zeta_ok;
-            if (strict) a.nsteps = 1;   // only the first step can see |v| > 1: run it alone with the literal statements
-            if (nt == 512) launch_c<512>(a, strict);
-            else launch_c<1024>(a, strict);
-            done += a.nsteps;
-            if (strict && zeta_ok) need_rterm = false;
-            ++launches;
+            a.stop_key = stop_key;
+            if (!zeta_ok || (need_rterm && !oor_valid)) {   // the literal statements, one step per launch
+                a.nsteps = 1;
+                go(a, true);
+                done += 1;
+                if (zeta_ok) need_rterm = false;
+            } else if (need_rterm) {                        // first launch after an import: STRICT / fast pair keyed on *oor
+                CTileArgs<T> s1 = a;
+                s1.nsteps = 1;
+                s1.oor = oor.p;
+                go(s1, true);
+                a.oor = oor.p;
+                go(a, false);
+                done += k;
+                need_rterm = false;
+            } else {
+                go(a, false);
+                done += k;
+            }
         }
         ODESAT_CUDA(cudaGetLastError());
         return launches;

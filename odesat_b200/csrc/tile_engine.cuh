@@ -50,7 +50,28 @@ template <typename T> struct TileArgs {
     int32_t* solved = nullptr;
     T dt = T(0), zeta = T(0), xl_max = T(0);
     int32_t step0 = 0, nsteps = 0, freeze = 0;
+    // `inter` early exit without a host round trip: the (all-reduced) key of the PREVIOUS chunk; when it names a
+    // flagged replica this speculatively issued launch does nothing.
+    const unsigned long long* stop_key = nullptr;
+    // Device-side choice between the literal first step and the fast arithmetic: *oor != 0 ⇔ the imported state
+    // holds a value outside the domain on which the two are bit-identical.  The first launch after an import is
+    // issued as a PAIR: the STRICT kernel (one step; a no-op when *oor == 0) and the fast kernel (which skips the
+    // step the STRICT kernel has taken when *oor != 0) — no device→host flag read in between.
+    const unsigned* oor = nullptr;
 };
+
+constexpr unsigned long long KEY_NONE = 0x7FFFFFFFFFFFFFFFull;   // INT64_MAX: no replica has flagged
+
+// Common prologue of the step kernels: → first step index this launch runs (nsteps = nothing to do).
+template <bool STRICT, typename A> __device__ __forceinline__ int launch_first_step(const A& a) {
+    if (a.stop_key != nullptr && *a.stop_key != KEY_NONE) return a.nsteps;
+    if (a.oor != nullptr) {
+        const unsigned o = *a.oor;
+        if (STRICT) return o ? 0 : a.nsteps;
+        return o ? 1 : 0;
+    }
+    return 0;
+}
 
 template <typename T, int W> struct RowIO;
 template <> struct RowIO<float, 2> {
@@ -276,6 +297,8 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
     uint2* ring_e = reinterpret_cast<uint2*>(ring_m + D * NT);
     uint2* s_items = reinterpret_cast<uint2*>(ring_e + (ER ? D * NT : 0));   // {slot base, count | last << 31}
 
+    const int s_first = launch_first_step<STRICT>(a);   // block-uniform
+    if (s_first >= a.nsteps) return;
     const unsigned tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
     T* vt = a.vt + tile * a.N * W;
@@ -317,7 +340,7 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
     uint2 e_next = make_uint2(0u, 0u);
     if (!ER && tid < (it_next.y & 0x7FFFFFFFu)) e_next = __ldg(at8(my_entry, it_next.x));
 
-    for (int s = 0; s < a.nsteps; ++s) {
+    for (int s = s_first; s < a.nsteps; ++s) {
         bool all_frozen = true;
 #pragma unroll
         for (int w = 0; w < W; ++w) all_frozen = all_frozen && frozen[w];
@@ -473,6 +496,8 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed_tma(const TileArgs<T> a) {
     const int n_items = a.n_items;                             // a multiple of D (host-checked)
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(s_items + n_items + 2);
 
+    const int s_first = launch_first_step<false>(a);   // block-uniform
+    if (s_first >= a.nsteps) return;
     const unsigned tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
     T* vt = a.vt + tile * a.N * W;
@@ -517,7 +542,7 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed_tma(const TileArgs<T> a) {
     }
     unsigned parity = 0;   // bit k: phase the consumers of stage k wait for next
 
-    for (int s = 0; s < a.nsteps; ++s) {
+    for (int s = s_first; s < a.nsteps; ++s) {
         bool all_frozen = true;
 #pragma unroll
         for (int w = 0; w < W; ++w) all_frozen = all_frozen && frozen[w];
@@ -638,6 +663,8 @@ __global__ void __launch_bounds__(32) k_tile_small(const TileArgs<T> a) {
     uint2* entries = reinterpret_cast<uint2*>(cells + (size_t)n_items * 32);
     uint2* s_items = entries + (size_t)n_items * 32;
 
+    const int s_first = launch_first_step<STRICT>(a);
+    if (s_first >= a.nsteps) return;
     const unsigned lane = threadIdx.x;
     const int64_t tile = blockIdx.x;
     T* vt = a.vt + tile * a.N * W;
@@ -672,7 +699,7 @@ __global__ void __launch_bounds__(32) k_tile_small(const TileArgs<T> a) {
     }
     __syncwarp();
 
-    for (int s = 0; s < a.nsteps; ++s) {
+    for (int s = s_first; s < a.nsteps; ++s) {
         bool all_frozen = true;
 #pragma unroll
         for (int w = 0; w < W; ++w) all_frozen = all_frozen && frozen[w];
@@ -783,13 +810,16 @@ __global__ void k_tile_import(const T* __restrict__ v, const T* __restrict__ xs,
         const int64_t slot = row - N;
         const int m = perm[slot];
         T a[W], b[W];
+        bool bad = false;
 #pragma unroll
         for (int w = 0; w < W; ++w) {
             const int64_t r = tile * W + w;
             const bool ok = m >= 0 && r < R;
             a[w] = ok ? xs[(int64_t)m * Rp + r] : T(0);
             b[w] = ok ? xl[(int64_t)m * Rp + r] : T(0);
+            bad = bad || !mem_in_fast_domain(a[w]) || !mem_in_fast_domain(b[w]);
         }
+        if (bad) *out_of_range = 1u;
         mem[tile * Mpad + slot] = IO::pack_mem(a, b);
     }
 }
@@ -907,7 +937,13 @@ template <typename T> struct TileBase {
     virtual void reset_control() = 0;
     virtual int64_t import_state(const T* v, const T* xs, const T* xl, int64_t Rp) = 0;   // canonical [row][Rp] → tile layout
     virtual int64_t export_state(T* v, T* xs, T* xl, int64_t Rp) = 0;
-    virtual int64_t run_fixed(T dt, T zeta, int64_t n, int freeze, int32_t* solved, int64_t step0) = 0;   // → launches
+    // enqueues n fixed steps (no host synchronisation); stop_key: see TileArgs; → launches
+    virtual int64_t run_fixed(T dt, T zeta, int64_t n, int freeze, int32_t* solved, int64_t step0,
+                              const unsigned long long* stop_key = nullptr) = 0;
+    // device-to-device copy of the whole tile-layout state, and back (lock-step `inter`: a chunk that overshot the
+    // winning step is replayed from the chunk's start)
+    virtual void snapshot() = 0;
+    virtual void restore() = 0;
     // Optional shortcuts that work on the tile layout directly (no canonical round trip); 0 = not offered.
     virtual bool has_direct() const { return false; }
     virtual int64_t init_mem(const int8_t* /*xs0*/) { return 0; }                                   // xs = xs0, xl = 1 for every replica
@@ -925,10 +961,12 @@ template <typename T> struct TileEngine final : TileBase<T> {
     int64_t R, tiles;
     std::shared_ptr<TileSchedule> sched;
     cudaStream_t stream;
-    DevBuf<T> vt;
-    DevBuf<Mem> mem;
-    DevBuf<unsigned> oor;
-    bool need_rterm = true;
+    DevBuf<T> vt, vt_snap;
+    DevBuf<Mem> mem, mem_snap;
+    DevBuf<unsigned> oor;        // device flag set by the import kernels: the state needs the literal first step
+    bool need_rterm = true;      // the next launch is the first one after an import: issue the STRICT / fast pair
+    bool oor_valid = false;      // *oor was written by an import since the last reset (else: assume the worst)
+    int64_t* ledger_ = nullptr;
     // ring fed by cp.async.bulk (k_tile_fixed_tma).  Measured on B200 at the headline size, ms/step TMA vs per-thread
     // cp.async: BALANCED 768 threads f32 0.553 vs 0.589, f64 0.600 vs 0.629 (at 640) — the defaults below; f32 640
     // threads 0.592 vs 0.596; EXACT 512 threads 0.681 vs 0.636 — the elected-thread issue and the per-item barrier
@@ -966,7 +1004,7 @@ template <typename T> struct TileEngine final : TileBase<T> {
     }
     static bool preferred(const odesat_formula&, int64_t R) { return R >= 8; }
 
-    TileEngine(const odesat_formula& f_, int64_t R_, int kind, cudaStream_t st, int64_t* ledger) : f(f_), R(R_), stream(st) {
+    TileEngine(const odesat_formula& f_, int64_t R_, int kind, cudaStream_t st, int64_t* ledger) : f(f_), R(R_), stream(st), ledger_(ledger) {
         tiles = (R + W - 1) / W;
         // levels: BALANCED colour classes do not depend on the CTA width; EXACT levels are list-scheduled
         // with the CTA width as the cap (one item per level), so they are built per candidate width
@@ -1045,11 +1083,27 @@ template <typename T> struct TileEngine final : TileBase<T> {
         sched = it->second;
         if (smem_bytes(f.N, sched->n_items, nt, depth) > kMaxSmem) throw Error(ODESAT_EUNSUPPORTED, "schedule does not fit in shared memory");
         use_tma = tma_env >= 0 ? tma_env == 1 : (kind == ODESAT_SCHED_BALANCED && nt == 768 && depth % 3 == 0);
+        {   // the TMA kernel orders a slot's write-back against its next bulk read with a proxy fence issued at the start
+            // of the next NON-EMPTY item: at least one such item must lie between the write and the wrap-around refill
+            int real = 0;
+            for (uint32_t it : sched->items) real += ((it >> 20) & 0x7FFu) != 0u;
+            if (real < 2 * depth + 2) use_tma = false;
+        }
         vt.alloc((size_t)(tiles * f.N * W), ledger);
         mem.alloc((size_t)(tiles * sched->Mpad), ledger);
         oor.alloc(1, ledger);
     }
-    void reset_control() override { need_rterm = true; }
+    void reset_control() override { need_rterm = true; oor_valid = false; }
+    void snapshot() override {
+        if (!vt_snap.p) { vt_snap.alloc(vt.n, ledger_); mem_snap.alloc(mem.n, ledger_); }
+        ODESAT_CUDA(cudaMemcpyAsync(vt_snap.p, vt.p, vt.bytes(), cudaMemcpyDeviceToDevice, stream));
+        ODESAT_CUDA(cudaMemcpyAsync(mem_snap.p, mem.p, mem.bytes(), cudaMemcpyDeviceToDevice, stream));
+    }
+    void restore() override {
+        ODESAT_REQUIRE(vt_snap.p != nullptr, "restore without a snapshot");
+        ODESAT_CUDA(cudaMemcpyAsync(vt.p, vt_snap.p, vt.bytes(), cudaMemcpyDeviceToDevice, stream));
+        ODESAT_CUDA(cudaMemcpyAsync(mem.p, mem_snap.p, mem.bytes(), cudaMemcpyDeviceToDevice, stream));
+    }
 
     void geom(int64_t rows, dim3& grid, dim3& block) const {
         int bx = 1;
@@ -1064,11 +1118,9 @@ template <typename T> struct TileEngine final : TileBase<T> {
         dim3 g, b;
         geom(f.N + sched->Mpad, g, b);
         k_tile_import<T><<<g, b, 0, stream>>>(v, xs, xl, Rp, R, f.N, sched->Mpad, sched->d_perm.p, vt.p, mem.p, tiles, oor.p);
-        unsigned h = 0;
-        ODESAT_CUDA(cudaMemcpyAsync(&h, oor.p, 4, cudaMemcpyDeviceToHost, stream));
-        ODESAT_CUDA(cudaStreamSynchronize(stream));
         ODESAT_CUDA(cudaGetLastError());
-        need_rterm = h != 0;
+        need_rterm = true;    // decided on the device: the next launch is the STRICT / fast pair keyed on *oor
+        oor_valid = true;
         return 1;
     }
     int64_t export_state(T* v, T* xs, T* xl, int64_t Rp) override {
@@ -1090,11 +1142,9 @@ template <typename T> struct TileEngine final : TileBase<T> {
         ODESAT_CUDA(cudaMemsetAsync(oor.p, 0, 4, stream));
         dim3 g((unsigned)((f.N + 31) / 32), (unsigned)((tiles * W + 31) / 32)), b(32, 8);
         k_tile_import_v<T><<<g, b, 0, stream>>>(v, Rp, R, f.N, vt.p, tiles, oor.p);
-        unsigned h = 0;
-        ODESAT_CUDA(cudaMemcpyAsync(&h, oor.p, 4, cudaMemcpyDeviceToHost, stream));
-        ODESAT_CUDA(cudaStreamSynchronize(stream));
         ODESAT_CUDA(cudaGetLastError());
-        need_rterm = h != 0;
+        need_rterm = true;
+        oor_valid = true;
         return 1;
     }
     int64_t verify_direct(uint32_t* bad) override {
@@ -1152,7 +1202,8 @@ template <typename T> struct TileEngine final : TileBase<T> {
         else launch_d<1024>(a, strict);
     }
 
-    int64_t run_fixed(T dt, T zeta, int64_t n, int freeze, int32_t* solved, int64_t step0) override {
+    int64_t run_fixed(T dt, T zeta, int64_t n, int freeze, int32_t* solved, int64_t step0,
+                      const unsigned long long* stop_key = nullptr) override {
         int64_t launches = 0;
         const bool zeta_ok = std::isfinite((double)zeta);
         for (int64_t done = 0; done < n;) {
@@ -1163,17 +1214,31 @@ template <typename T> struct TileEngine final : TileBase<T> {
             a.vt = vt.p; a.mem = mem.p; a.solved = solved;
             a.dt = dt; a.zeta = zeta; a.xl_max = T(1e4) * T(f.M);
             a.step0 = (int32_t)(step0 + done); a.nsteps = (int32_t)k; a.freeze = freeze;
-            if (need_rterm || !zeta_ok) {
-                // only the first step can see |v| > 1; run it alone with the literal rigidity term
+            a.stop_key = stop_key;
+            if (!zeta_ok || (need_rterm && !oor_valid)) {
+                // non-finite zeta (every step) or a state of unknown provenance (first step): the literal statements
                 a.nsteps = 1;
                 launch_nt(a, true);
                 done += 1;
                 if (zeta_ok) need_rterm = false;
+                ++launches;
+            } else if (need_rterm) {
+                // first launch after an import: only its first step can see a value outside the fast domain; the
+                // device flag decides which kernel of the pair takes it (TileArgs::oor)
+                TileArgs<T> s1 = a;
+                s1.nsteps = 1;
+                s1.oor = oor.p;
+                launch_nt(s1, true);
+                a.oor = oor.p;
+                launch_nt(a, false);
+                done += k;
+                need_rterm = false;
+                launches += 2;
             } else {
                 launch_nt(a, false);
                 done += k;
+                ++launches;
             }
-            ++launches;
         }
         ODESAT_CUDA(cudaGetLastError());
         return launches;

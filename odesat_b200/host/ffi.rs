@@ -25,11 +25,14 @@ pub struct OdesatParams {
     pub engine: i32,             // 0 = auto
     pub schedule: i32,           // 0 = exact summation order, 1 = balanced
     pub chunk: i32,              // steps between early-exit polls; <= 0 = 32
+    pub n_gpus: i32,             // replica batches: devices of this process to shard over; <= 0 = 1
+    pub sub_batches: i32,        // shards per device (upload / compute overlap); <= 0 = auto
 }
 
 #[link(name = "odesat_b200")]
 extern "C" {
     fn odesat_last_error() -> *const c_char;
+    fn odesat_device_count() -> c_int;
     fn odesat_formula_create(varnum: i64, n_clauses: i64, clause_off: *const i64, lits: *const i32,
                              out: *mut *mut OdesatFormula) -> c_int;
     fn odesat_formula_destroy(f: *mut OdesatFormula);
@@ -60,6 +63,8 @@ fn params(tolerance: Option<f64>, step_size: Option<f64>, steps: Option<usize>, 
         steps: steps.map(|s| s as i64).unwrap_or(-1),
         learning_rate: learning_rate.unwrap_or(f64::NAN),
         precision: 0, engine: 0, schedule: 0, chunk: 0,
+        // `batch` / `inter` replicas are independent: one process drives every visible GPU (single-state calls ignore it)
+        n_gpus: unsafe { odesat_device_count() }.max(1), sub_batches: 0,
     }
 }
 

@@ -4,7 +4,8 @@
 // (cnf.rs:138-219, 246-264, 289-315) so the GPU path is runnable end to end without the Rust crate.
 // `solve` runs the reference's ratio preprocessing first (`-r`, default 7.0, main.rs:150-166; restated in
 // preprocess.hpp) and replays the elimination trace on the result (main.rs:186-187).  Not restated:
-// `stoch`.  Extra flags: --seed (the reference's RNG is OS-seeded), --f32.
+// `stoch`.  Extra flags: --seed (the reference's RNG is OS-seeded), --f32, --gpus N (replica shards of `batch` /
+// `inter` over N devices of this process; default: every visible device), --chunk K (steps between early-exit polls).
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -80,7 +81,7 @@ static bool evaluate_cnf(std::map<std::size_t, bool>& values, const std::vector<
 }
 
 static int usage() {
-    std::fprintf(stderr, "usage: odesat_b200_cli <solve|batch|inter> -f FILE [-o OUT] [-t TOL] [-n STEPS] [-s STEP] [-l ZETA] [-r RATIO] [-b BATCH] [--seed S] [--f32]\n");
+    std::fprintf(stderr, "usage: odesat_b200_cli <solve|batch|inter> -f FILE [-o OUT] [-t TOL] [-n STEPS] [-s STEP] [-l ZETA] [-r RATIO] [-b BATCH] [--seed S] [--f32] [--gpus N] [--chunk K]\n");
     return 2;
 }
 
@@ -93,6 +94,7 @@ int main(int argc, char** argv) {
     std::size_t batch = 0;
     uint64_t seed = 1;
     bool f32 = false;
+    int gpus = 0, chunk = 0;                                                // 0: every visible device / library default
     double ratio = 7.0;                                                     // main.rs:150-154
     for (int i = 2; i < argc; ++i) {
         const std::string a = argv[i];
@@ -106,6 +108,8 @@ int main(int argc, char** argv) {
         else if (a == "-b" || a == "--batch-size") batch = (std::size_t)std::atoll(next());
         else if (a == "--seed") seed = (uint64_t)std::atoll(next());
         else if (a == "--f32") f32 = true;
+        else if (a == "--gpus") gpus = std::atoi(next());
+        else if (a == "--chunk") chunk = std::atoi(next());
         else if (a == "-r" || a == "--ctv-ratio") ratio = std::atof(next());
         else return usage();
     }
@@ -166,7 +170,10 @@ int main(int argc, char** argv) {
         std::printf("Simulating...\n");
         odesat_params p = system::make_params(tol, step, steps, zeta);
         p.precision = f32 ? ODESAT_F32 : ODESAT_F64;
+        p.chunk = chunk;
         const int64_t R = cmd == "solve" ? 1 : (int64_t)batch;
+        // replicas are independent (main.rs:278-308, system.rs:279-289): shard them over the devices of this process
+        p.n_gpus = cmd == "solve" ? 1 : (gpus > 0 ? gpus : std::max(1, odesat_device_count()));
         const int mode = cmd == "inter" ? ODESAT_MODE_INTER : ODESAT_MODE_BATCH;
         if (cmd == "solve" && !steps) p.steps = 1 << 30;   // the reference loops forever on UNSAT input
         std::vector<uint8_t> assignment(f.varnum), verified((std::size_t)R);
@@ -189,9 +196,10 @@ int main(int argc, char** argv) {
         std::fprintf(stderr, "[odesat_b200] replicas=%lld steps_run=%lld winner=%lld\n", (long long)R, (long long)run, (long long)winner);
         // one JSON record of the integration (the driver reports throughput next to the reference's lines)
         std::fprintf(stderr, "{\"variables\": %zu, \"clauses\": %zu, \"replicas\": %lld, \"steps_run\": %lld, \"seconds\": %.6f, "
-                             "\"clause_evals_per_s\": %.4g, \"precision\": \"%s\"}\n",
+                             "\"clause_evals_per_s\": %.4g, \"precision\": \"%s\", \"gpus\": %d}\n",
                      f.varnum, f.clauses.size(), (long long)R, (long long)run, sec,
-                     sec > 0 ? (double)run * (double)f.clauses.size() * (double)R / sec : 0.0, f32 ? "f32" : "f64");
+                     sec > 0 ? (double)run * (double)f.clauses.size() * (double)R / sec : 0.0, f32 ? "f32" : "f64",
+                     (int)std::min<int64_t>(p.n_gpus, R));
         std::printf("Rendering variable assignments...\n");
         std::string render;                                              // cnf.rs:289-298
         for (const auto& kv : values) render += std::to_string(kv.first) + " " + (kv.second ? "1" : "0") + "\n";

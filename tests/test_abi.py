@@ -28,12 +28,13 @@ def test_every_declared_symbol_is_exported():
     lib = C.CDLL(str(L.SO_PATH))
     for name in declared_functions():
         assert hasattr(lib, name), f"{name} declared in the header but not exported by the .so"
-    assert L.lib().odesat_abi_version() == 1
+    assert L.lib().odesat_abi_version() == 2
 
 
 def test_params_struct_layout_matches_header():
-    assert C.sizeof(L.Params) == 48
+    assert C.sizeof(L.Params) == 56
     p = L.make_params(step_size=0.01, steps=7)
+    assert p.n_gpus == 1 and p.sub_batches == 0
     assert p.steps == 7 and p.step_size == 0.01 and np.isnan(p.tolerance) and np.isnan(p.learning_rate)
 
 
