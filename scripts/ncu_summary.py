@@ -30,18 +30,40 @@ def main():
     for rep in sys.argv[1:]:
         raw = ncu_csv(rep, "raw")
         hdr, units = raw[0], raw[1]
+        # The source page prints one block per (launch, view) — with --import-source on there are TWO views per launch
+        # (SASS and the high-level source), each introduced by a "Kernel Name" row — in launch order.  Pair the blocks
+        # with the launches by position and keep, per launch, the view whose "Source" column holds SASS.
         src = ncu_csv(rep, "source")
-        blocks, cur = [], None
+        views, cur = [], None
         for r in src:
             if r and r[0] == "Kernel Name":
-                cur = []
-                blocks.append(cur)
+                cur = {"name": r[1] if len(r) > 1 else "", "rows": []}
+                views.append(cur)
             elif cur is not None:
-                cur.append(r)
+                cur["rows"].append(r)
+        n_launch = max(len(raw) - 2, 1)
+        per = max(len(views) // n_launch, 1)
+
+        def looks_like_sass(view):
+            rows = view["rows"]
+            if len(rows) < 2 or "Source" not in rows[0]:
+                return 0
+            i = rows[0].index("Source")
+            ops = [r[i].strip().split(" ")[0].lstrip("@!UP0123456789T ") for r in rows[1:40] if len(r) > i]
+            return sum(1 for o in ops if o[:3].isupper() or o.split(".")[0].isupper())
+        blocks = []
+        for k in range(n_launch):
+            cand = views[k * per:(k + 1) * per]
+            best = max(cand, key=looks_like_sass) if cand else None
+            blocks.append(best["rows"] if best else [])
         for k, vals in enumerate(raw[2:]):
             d = dict(zip(hdr, vals))
             u = dict(zip(hdr, units))
             print(f"== {rep.split('/')[-1]}  launch {k}: {d.get('Kernel Name')}")
+            base = lambda n: n.split("<")[0].split("(")[0].split("::")[-1].split(" ")[-1]
+            if k < len(blocks) and per * k < len(views) and views[per * k]["name"] and base(d.get("Kernel Name", "")) != base(views[per * k]["name"]):
+                print(f"   (source view belongs to {views[per * k]['name']!r}: pairing by position failed, SASS lines omitted)")
+                blocks[k] = []
             for key in KEYS:
                 if key in d and d[key] != "":
                     print(f"{key:75s} {d[key]:>18s} {u.get(key, '')}")

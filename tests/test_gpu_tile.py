@@ -216,3 +216,49 @@ def test_tma_fed_kernel_equals_the_per_thread_ring_at_the_bench_configuration(mo
     tol = dict(rtol=1e-5, atol=1e-6) if prec == L.F32 else dict(rtol=1e-12, atol=1e-15)
     np.testing.assert_allclose(g[0], o[0], **tol)
     assert eq(g[1], o[1]) and eq(g[2], o[2])
+
+
+def test_hundred_step_tolerance_of_the_benched_configuration():
+    """north_star: "fixed-step trajectories must agree over 100 steps within a stated tolerance".  For the configuration
+    bench.py times — f32, BALANCED schedule, the TMA-fed kernel, the N = 10 000 / alpha = 4.3 formula of BASELINE
+    configs[2] — the STATED bound against the f32 oracle after 100 steps of dt = 0.01 is
+        max |dv| <= 2e-5,  max |dxs| <= 2e-5,  max |xl / xl_ref - 1| <= 2e-5.
+    BALANCED differs from the reference only in the order in which a variable's clause contributions are added; on the
+    CPU, two f32 oracle runs that differ only in that order (clauses permuted) are 8e-7 / 1.4e-6 / 1.2e-6 apart after
+    100 steps and 7e-5 after 300 (the dynamics switch on argmin, so rounding differences grow), which is where the
+    bound comes from.  The EXACT schedule has no such term: bit-identical (test_long_trajectory_stays_bit_identical)."""
+    f = cnf.random_ksat(10_000, 4.3, seed=20240611 + 2)          # bench.py's formula
+    D = S.DeviceFormula(f)
+    F = O.OracleFormula(f.varnum, f.clause_off, f.lits)
+    R = 64
+    v, xs, xl = F.init_batch(1, R, np.float32)
+    b = B.ReplicaBatch(D, R, L.F32, L.ENGINE_TILE, L.SCHED_BALANCED)
+    b.upload(v, xs, xl)
+    b.run_fixed(0.01, f.default_zeta(), 100, freeze=False)
+    gv, gxs, gxl = b.download()
+    b.close()
+    F.batch_fixed(v, xs, xl, 0.01, f.default_zeta(), 100, freeze=False, nthreads=O.host_cores())
+    dv, dxs, dxl = np.abs(gv - v).max(), np.abs(gxs - xs).max(), np.abs(gxl / xl - 1).max()
+    print(f"100-step deviation of the benched configuration vs the f32 oracle: v {dv:.3g} xs {dxs:.3g} xl(rel) {dxl:.3g}")
+    assert dv <= 2e-5 and dxs <= 2e-5 and dxl <= 2e-5
+    assert dv > 0                                                  # it IS a different summation order
+
+
+def test_tma_ring_soak_4096_replicas_1024_steps(monkeypatch):
+    """Race evidence in lieu of compute-sanitizer (closed on this pool): the TMA-fed kernel (bulk copies + mbarriers +
+    cross-proxy fences) and the per-thread cp.async ring integrate the full bench batch — 4 096 replicas, N = 10 000 —
+    for 1 024 steps (16 launches of 64 steps, ring wrap-arounds across steps and launches) and must end BIT-IDENTICAL."""
+    f = cnf.random_ksat(10_000, 4.3, seed=20240611 + 2)
+    D = S.DeviceFormula(f)
+    R = 4096
+    out = {}
+    for tma in ("1", "0"):
+        monkeypatch.setenv("ODESAT_TILE_TMA", tma)
+        b = B.ReplicaBatch(D, R, L.F32, L.ENGINE_TILE, L.SCHED_BALANCED)
+        b.init(1, 0)
+        b.run_fixed(0.01, f.default_zeta(), 1024, freeze=False)
+        out[tma] = b.download()
+        b.close()
+    for a, c in zip(out["1"], out["0"]):
+        assert eq(a, c)
+    assert (np.abs(out["1"][0]) == 1).mean() > 0.02
