@@ -275,7 +275,7 @@ def run_reference(args):
                          "single_core": {"value": single, "unit": "clause-evals/s", "cores": 1, "sample": single_desc}},
         "e2e": {"value": value, "unit": "clause-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    }), flush=True)
 
 
 def measure_inter(args, torch, dist, rank, world, local, dev, barrier):
@@ -337,6 +337,9 @@ def measure_inter(args, torch, dist, rank, world, local, dev, barrier):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_c, ms_n = float(t[0]), float(t[1])
     eng = {L.ENGINE_GATHER: "gather", L.ENGINE_TILE: "tile"}[b.engine]
+    # the pinned block and the events were used on the batch's stream: release them while that stream still exists
+    del host, keys, evs, t
+    torch.cuda.synchronize()
     b.close()
     steps = chunk * chunks
     bytes_step = algorithmic_bytes_per_step(f.varnum, f.n_clauses, f.n_literals, R, 4)
@@ -538,7 +541,7 @@ def run_gpu(args):
             out["collective"] = inter["collective"]
         if cpu is not None:
             out["cpu_baseline"] = cpu
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

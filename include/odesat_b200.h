@@ -214,6 +214,28 @@ int odesat_simulate_inter(const odesat_formula* f, int64_t R, double* v, double*
                           const odesat_params* params, uint8_t* assignment, int64_t* winner,
                           int64_t* steps_taken);
 
+/* ---- stochastic local search: src/stoch.rs (a separate algorithm with the same data layout) ----
+ * State (stoch.rs:8-12): v[N] bool as uint8, xl[M] uint64.  The reference draws its flips from an OS-seeded ThreadRng
+ * (stoch.rs:68, :81 — unreproducible by construction); here r = 1 + mulhi64(SplitMix64(seed, replica, step, variable),
+ * total), the same function as the CPU oracle.  A variable that occurs in no clause never flips (the reference panics
+ * on the empty range 1..=0).
+ *
+ * stoch.rs:26-31 step(&mut State, &CNFFormula, &mut SlabState, &mut ThreadRng) -> bool: one step on a caller-owned
+ * state, in place; step_index selects the random draws; *allsat = the step's return value. */
+int odesat_stoch_step(const odesat_formula* f, uint8_t* v, uint64_t* xl, uint64_t seed, int64_t replica,
+                      int64_t step_index, int* allsat);
+/* stoch.rs:80 search(&CNFFormula, Option<usize>) -> Vec<bool> for R independent replicas on the device.
+ *  v / xl      : host [R][N] uint8 / [R][M] uint64 initial states, or NULL for the reference's (false / 1, :84-87);
+ *                written back when write_back != 0
+ *  steps       : < 0 → run until some replica's step returns true (stoch.rs:101-105)
+ *  The loop ends after the first chunk of `chunk` steps (<= 0 → 64) in which some replica flagged; a flagged replica
+ *  stops stepping (search's `break`).  winner = lowest replica flagged at the earliest step, -1 when none;
+ *  assignment[N] = its v (replica 0's when none); verified[r] = replica r's v satisfies the CNF (cnf.rs:246-264). */
+int odesat_stoch_search(const odesat_formula* f, int64_t R, uint8_t* v, uint64_t* xl, uint64_t seed,
+                        int64_t replica_offset, int64_t steps, int32_t chunk, int32_t write_back,
+                        int64_t* solved_step, uint8_t* verified, int64_t* winner, uint8_t* assignment,
+                        int64_t* steps_run);
+
 /* ---- diagnostics (host only, no device needed) -------------------------------------------------
  * Compiles the TILE engine's clause schedule for a formula and reports it: out[0] = levels,
  * out[1] = items, out[2] = clause slots (incl. padding), out[3] = 1000 x the average number of

@@ -91,6 +91,8 @@ _SIGS = {
     "odesat_simulate_batch_f32": [_P, _I64, _P, _P, _P, C.c_uint64, _I64, C.POINTER(Params), _I32,
                                   _I32, _P, _P, _PI64, _P, _PI64],
     "odesat_simulate_inter": [_P, _I64, _P, _P, _P, C.POINTER(Params), _P, _PI64, _PI64],
+    "odesat_stoch_step": [_P, _P, _P, C.c_uint64, _I64, _I64, _PI],
+    "odesat_stoch_search": [_P, _I64, _P, _P, C.c_uint64, _I64, _I64, _I32, _I32, _P, _P, _PI64, _P, _PI64],
     "odesat_tile_schedule_stats": [_I64, _I64, _P, _P, _I32, _I32, _I32, _P, _I64, _P, _I64, _P],
     "odesat_batch_create": [_P, _I64, _I32, _I32, _I32, C.POINTER(_P)],
     "odesat_batch_destroy": [_P],

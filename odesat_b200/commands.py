@@ -18,6 +18,7 @@ import numpy as np
 from . import _lib as L
 from . import batch as B
 from . import cnf, preprocess
+from . import stoch as ST
 from .system import DeviceFormula, State, init_short_term_memory, simulate
 
 
@@ -104,6 +105,30 @@ def solve(input: str, output: Optional[str] = None, tolerance: Optional[float] =
     return _finish(values, original, output, log, res)
 
 
+def stoch(input: str, output: Optional[str] = None, step_number: Optional[int] = None, ctv_ratio: Optional[float] = None, *,
+          batch_size: int = 1, seed: int = 0, log: Callable[[str], None] = print) -> CommandResult:
+    """main.rs:206-252 (`odesat stoch -f F [-o O] [-n steps] [-r ratio]`): ratio preprocessing, then the weighted
+    random-flip search of src/stoch.rs on the GPU (`batch_size` independent replicas; the reference runs one), trace
+    replay, exact verification."""
+    ratio = 7.0 if ctv_ratio is None else ctv_ratio                              # main.rs:209-213
+    original = _read(input, log)
+    log("Preprocessing CNF formula...")
+    clauses, varnum, trace = preprocess.repeatedly_resolve_and_update(
+        preprocess.to_clause_set(original.clauses), original.varnum, ratio, log=log)
+    reduced = cnf.CNF([preprocess.sorted_literals(c) for c in preprocess.sorted_clauses(clauses)], varnum)
+    formula = cnf.normalize_cnf_variables(reduced)
+    log("Simulating...")
+    F = DeviceFormula(formula)
+    r = ST.search_batch(F, batch_size, step_number, seed=seed)
+    F.close()
+    log("Mapping values...")
+    values = formula.map_values_by_indices(r.assignment)
+    preprocess.calculate_trace(values, trace)                                    # main.rs:237-238
+    log("Evaluating CNF formula...")
+    res = CommandResult(False, {}, "", steps=r.steps_run, winner=r.winner, n_vars=formula.varnum, n_clauses=formula.n_clauses)
+    return _finish(values, original, output, log, res)
+
+
 def batch(input: str, step_number: int, batch_size: int, output: Optional[str] = None,
           tolerance: Optional[float] = None, step_size: Optional[float] = None,
           learning_rate: Optional[float] = None, *, seed: int = 0, precision: int = L.F64,
@@ -114,6 +139,16 @@ def batch(input: str, step_number: int, batch_size: int, output: Optional[str] =
     log("Normalizing CNF formula...")
     formula = cnf.normalize_cnf_variables(original)
     log("Simulating...")
+    if batch_size == 0:   # main.rs:276-308: the loop does not run — empty map, is_satisfiable stays false
+        res = CommandResult(False, {}, "", n_vars=formula.varnum, n_clauses=formula.n_clauses)
+        log("\nChecking if solution vector satisfies formula: false")
+        log("Rendering variable assignments...")
+        if output is not None:
+            log("Writing results to file...")
+            open(output, "w").close()
+        else:
+            log("Variable assignments:\n")
+        return res
     F = DeviceFormula(formula)
     r = B.simulate_batch(F, batch_size, seed=seed, tolerance=tolerance, step_size=step_size, steps=step_number,
                          learning_rate=learning_rate, precision=precision, mode=L.MODE_BATCH)
@@ -134,6 +169,8 @@ def inter(input: str, batch_size: int, output: Optional[str] = None, tolerance: 
     log("Normalizing CNF formula...")
     formula = cnf.normalize_cnf_variables(original)
     log("Simulating...")
+    if batch_size == 0:
+        raise ValueError("inter needs at least one replica (the reference indexes states[0], system.rs:357)")
     F = DeviceFormula(formula)
     r = B.simulate_batch(F, batch_size, seed=seed, tolerance=tolerance, step_size=step_size,
                          steps=step_number, learning_rate=learning_rate, precision=precision, mode=L.MODE_INTER)

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "batch.cuh"
+#include "stoch.cuh"
 
 using namespace odesat;
 
@@ -432,6 +433,40 @@ template <typename TH> void xs0_impl(const odesat_formula* f, TH* xs0) {
     for (int64_t m = 0; m < f->M; ++m) xs0[m] = (TH)f->h_xs0[m];   // system.rs:362-372 (host-side, O(L) at create)
 }
 
+void stoch_search_impl(const odesat_formula* f, int64_t R, uint8_t* v, uint64_t* xl, uint64_t seed, int64_t replica_offset,
+                       int64_t steps, int chunk, int write_back, int64_t* solved_step, uint8_t* verified, int64_t* winner,
+                       uint8_t* assignment, int64_t* steps_run) {
+    ODESAT_REQUIRE(f != nullptr, "formula is NULL");
+    ODESAT_REQUIRE(R >= 0, "negative replica count");
+    require_device();
+    if (R == 0) {
+        if (winner) *winner = -1;
+        if (steps_run) *steps_run = 0;
+        if (assignment) std::memset(assignment, 0, (size_t)f->N);
+        return;
+    }
+    DeviceGuard guard(f->device);
+    StochBatch b(f, R);
+    if (v || xl) b.upload(v, reinterpret_cast<const unsigned long long*>(xl));
+    if (chunk <= 0) chunk = 64;
+    int64_t key = NO_KEY;
+    while (steps < 0 || b.step < steps) {                                        // stoch.rs:94-106
+        b.run(seed, replica_offset, steps < 0 ? chunk : std::min<int64_t>(chunk, steps - b.step));
+        key = b.first_key();
+        if (key != NO_KEY) break;
+    }
+    std::vector<int64_t> solved((size_t)R, -1);
+    b.status(solved.data());
+    const int64_t win = key != NO_KEY ? (key & 0xFFFFFFFFll) : -1;
+    if (key != NO_KEY) for (int64_t q = 0; q < R; ++q) if (solved[q] > (key >> 32)) solved[q] = -1;
+    if (solved_step) for (int64_t q = 0; q < R; ++q) solved_step[q] = solved[q];
+    if (verified) b.verify(verified);                                            // cnf.rs:246-264
+    if (winner) *winner = win;
+    if (assignment) b.assignment(win >= 0 ? win : 0, assignment);                // stoch.rs:109
+    if (steps_run) *steps_run = key != NO_KEY ? (key >> 32) + 1 : b.step;
+    if (write_back) b.download(v, reinterpret_cast<unsigned long long*>(xl));
+}
+
 }  // namespace
 
 extern "C" {
@@ -546,6 +581,32 @@ int odesat_simulate_inter(const odesat_formula* f, int64_t R, double* v, double*
         ODESAT_REQUIRE(v && xs && xl, "simulate_inter takes caller-supplied states");
         simulate_batch_impl<double>(f, R, v, xs, xl, 0, 0, params, ODESAT_MODE_INTER, 1, nullptr, nullptr, winner, assignment,
                                     steps_taken);
+    });
+}
+
+int odesat_stoch_step(const odesat_formula* f, uint8_t* v, uint64_t* xl, uint64_t seed, int64_t replica, int64_t step_index,
+                      int* allsat) {
+    return guarded([&] {
+        ODESAT_REQUIRE(f && v && xl, "NULL state or formula");
+        ODESAT_REQUIRE(step_index >= 0, "negative step index");
+        require_device();
+        DeviceGuard guard(f->device);
+        StochBatch b(f, 1);
+        b.upload(v, reinterpret_cast<const unsigned long long*>(xl));
+        b.step = step_index;
+        b.run(seed, replica, 1);
+        int64_t s = -1;
+        b.status(&s);
+        b.download(v, reinterpret_cast<unsigned long long*>(xl));
+        if (allsat) *allsat = s == step_index ? 1 : 0;
+    });
+}
+int odesat_stoch_search(const odesat_formula* f, int64_t R, uint8_t* v, uint64_t* xl, uint64_t seed, int64_t replica_offset,
+                        int64_t steps, int32_t chunk, int32_t write_back, int64_t* solved_step, uint8_t* verified,
+                        int64_t* winner, uint8_t* assignment, int64_t* steps_run) {
+    return guarded([&] {
+        stoch_search_impl(f, R, v, xl, seed, replica_offset, steps, chunk, write_back, solved_step, verified, winner, assignment,
+                          steps_run);
     });
 }
 

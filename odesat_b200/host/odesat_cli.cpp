@@ -1,10 +1,11 @@
-// odesat_cli.cpp — `solve` / `batch` / `inter` driver over libodesat_b200 with the reference's
+// odesat_cli.cpp — `solve` / `batch` / `inter` / `stoch` driver over libodesat_b200 with the reference's
 // flags (-f -o -t -n -s -l -b, main.rs:31-141) and console lines (main.rs:156-200, 263-320,
 // 335-383).  SURVEY §8f row 1: the DIMACS reader, normaliser and result writer are restated here
 // (cnf.rs:138-219, 246-264, 289-315) so the GPU path is runnable end to end without the Rust crate.
 // `solve` runs the reference's ratio preprocessing first (`-r`, default 7.0, main.rs:150-166; restated in
-// preprocess.hpp) and replays the elimination trace on the result (main.rs:186-187).  Not restated:
-// `stoch`.  Extra flags: --seed (the reference's RNG is OS-seeded), --f32, --gpus N (replica shards of `batch` /
+// preprocess.hpp) and replays the elimination trace on the result (main.rs:186-187).  `stoch` (main.rs:206-252) runs
+// the same preprocessing and then the weighted random-flip search of src/stoch.rs on the GPU (-b replicas; default 1).
+// Extra flags: --seed (the reference's RNG is OS-seeded), --f32, --gpus N (replica shards of `batch` /
 // `inter` over N devices of this process; default: every visible device), --chunk K (steps between early-exit polls).
 #include <algorithm>
 #include <chrono>
@@ -81,7 +82,7 @@ static bool evaluate_cnf(std::map<std::size_t, bool>& values, const std::vector<
 }
 
 static int usage() {
-    std::fprintf(stderr, "usage: odesat_b200_cli <solve|batch|inter> -f FILE [-o OUT] [-t TOL] [-n STEPS] [-s STEP] [-l ZETA] [-r RATIO] [-b BATCH] [--seed S] [--f32] [--gpus N] [--chunk K]\n");
+    std::fprintf(stderr, "usage: odesat_b200_cli <solve|stoch|batch|inter> -f FILE [-o OUT] [-t TOL] [-n STEPS] [-s STEP] [-l ZETA] [-r RATIO] [-b BATCH] [--seed S] [--f32] [--gpus N] [--chunk K]\n");
     return 2;
 }
 
@@ -137,7 +138,7 @@ int main(int argc, char** argv) {
         }
         return 0;
     }
-    if (input.empty() || (cmd != "solve" && cmd != "batch" && cmd != "inter")) return usage();
+    if (input.empty() || (cmd != "solve" && cmd != "batch" && cmd != "inter" && cmd != "stoch")) return usage();
     if ((cmd == "batch" || cmd == "inter") && batch == 0) return usage();
     if (cmd == "batch" && !steps) return usage();                       // main.rs:96-97: -n is required
     try {
@@ -151,7 +152,7 @@ int main(int argc, char** argv) {
         CNFFormula f = parse_dimacs_format(ss.str(), raw);
         prep::Trace trace;
         std::vector<std::vector<int>> integrated = raw;                     // the clauses the ODE is built from
-        if (cmd == "solve") {                                               // main.rs:162-166
+        if (cmd == "solve" || cmd == "stoch") {                             // main.rs:162-166, 223-226
             std::printf("Preprocessing CNF formula...\n");
             prep::ClauseSet set;
             for (const auto& c : raw) set.insert(prep::make_clause(c));
@@ -171,7 +172,7 @@ int main(int argc, char** argv) {
         odesat_params p = system::make_params(tol, step, steps, zeta);
         p.precision = f32 ? ODESAT_F32 : ODESAT_F64;
         p.chunk = chunk;
-        const int64_t R = cmd == "solve" ? 1 : (int64_t)batch;
+        const int64_t R = cmd == "solve" ? 1 : (cmd == "stoch" ? (int64_t)std::max<std::size_t>(batch, 1) : (int64_t)batch);
         // replicas are independent (main.rs:278-308, system.rs:279-289): shard them over the devices of this process
         p.n_gpus = cmd == "solve" ? 1 : (gpus > 0 ? gpus : std::max(1, odesat_device_count()));
         const int mode = cmd == "inter" ? ODESAT_MODE_INTER : ODESAT_MODE_BATCH;
@@ -181,18 +182,22 @@ int main(int argc, char** argv) {
         int64_t winner = -1, run = 0;
         // states are generated on the device (main.rs:283-289 with a seeded generator)
         const auto t0 = std::chrono::steady_clock::now();
-        system::check(odesat_simulate_batch(F.handle(), R, nullptr, nullptr, nullptr, seed, 0, &p, mode, 0, solved.data(),
-                                            verified.data(), &winner, assignment.data(), &run));
+        if (cmd == "stoch")   // stoch.rs:80-110 search, R independent replicas from the reference's initial state
+            system::check(odesat_stoch_search(F.handle(), R, nullptr, nullptr, seed, 0, steps ? (int64_t)*steps : -1, chunk, 0,
+                                              solved.data(), verified.data(), &winner, assignment.data(), &run));
+        else
+            system::check(odesat_simulate_batch(F.handle(), R, nullptr, nullptr, nullptr, seed, 0, &p, mode, 0, solved.data(),
+                                                verified.data(), &winner, assignment.data(), &run));
         const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         std::map<std::size_t, bool> values;                              // cnf.rs:301-315
         for (const auto& kv : name_map) values[kv.first] = assignment[kv.second] != 0;
-        if (cmd == "solve") {
+        if (cmd == "solve" || cmd == "stoch") {
             std::printf("Mapping values...\n");
             prep::calculate_trace(values, trace);                           // main.rs:186-187
             std::printf("Evaluating CNF formula...\n");
         }
         const bool ok = evaluate_cnf(values, raw);
-        std::printf("%sChecking if solution vector satisfies formula: %s\n", cmd == "solve" ? "" : "\n", ok ? "true" : "false");
+        std::printf("%sChecking if solution vector satisfies formula: %s\n", (cmd == "solve" || cmd == "stoch") ? "" : "\n", ok ? "true" : "false");
         std::fprintf(stderr, "[odesat_b200] replicas=%lld steps_run=%lld winner=%lld\n", (long long)R, (long long)run, (long long)winner);
         // one JSON record of the integration (the driver reports throughput next to the reference's lines)
         std::fprintf(stderr, "{\"variables\": %zu, \"clauses\": %zu, \"replicas\": %lld, \"steps_run\": %lld, \"seconds\": %.6f, "

@@ -245,9 +245,9 @@ inline uint64_t sm64(uint64_t x) {
     x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
     return x ^ (x >> 31);
 }
+inline uint64_t v0_key(uint64_t seed, uint64_t replica) { return sm64(seed ^ sm64(replica)); }
 inline uint64_t v0_bits(uint64_t seed, uint64_t replica, uint64_t var) {
-    const uint64_t key = sm64(seed ^ sm64(replica));
-    return sm64(key ^ (var * 0xD1342543DE82EF95ull));
+    return sm64(v0_key(seed, replica) ^ (var * 0xD1342543DE82EF95ull));
 }
 template <typename T> T v0_value(uint64_t bits);
 template <> double v0_value<double>(uint64_t bits) {
@@ -311,6 +311,60 @@ void batch_adaptive(const Formula& f, int64_t R, T* v, T* xs, T* xl, T tol, T ze
 }  // namespace
 
 #define F(p) (*static_cast<const Formula*>(p))
+
+// ---------------------------------------------------------------------------------------------
+// src/stoch.rs — the stochastic local search (a separate algorithm).
+// The reference draws `rng.gen_range(1..=total)` from an OS-seeded ThreadRng (stoch.rs:68, :81), which no run can
+// reproduce; the oracle and the GPU kernels share a counter-based stand-in: r = 1 + mulhi64(h, total) with
+// h = SplitMix64 of (seed, replica, step, variable).  Everything else is the reference's integer arithmetic.
+// ---------------------------------------------------------------------------------------------
+constexpr uint64_t STOCH_ALPHA = 20;                                       // stoch.rs:18
+inline uint64_t stoch_bits(uint64_t seed, uint64_t replica, uint64_t step, uint64_t var) {
+    return sm64(v0_key(seed, replica) ^ sm64(step + 0x632BE59BD9B4E019ull) ^ (var * 0xD1342543DE82EF95ull));
+}
+
+// stoch.rs:26-78 step → all clauses satisfied (by the state before the flips)
+bool stoch_step(const Formula& f, uint8_t* v, uint64_t* xl, uint64_t seed, uint64_t replica, uint64_t step,
+                std::vector<uint64_t>& unsat_w, std::vector<uint64_t>& total_w) {
+    bool all = true;                                                       // :32
+    unsat_w.assign((size_t)f.varnum, 0);                                   // :35-38 slab of (0, 0)
+    total_w.assign((size_t)f.varnum, 0);
+    for (int64_t m = 0; m < f.n_clauses; ++m) {                            // :41-64
+        bool sat = false;                                                  // :20-25 evaluate_clause
+        for (int64_t j = f.off[m]; j < f.off[m + 1]; ++j) sat = sat || ((v[f.var[j]] != 0) != (f.neg[j] != 0));
+        uint64_t x = xl[m];
+        if (sat) { x = x > 0 ? x - 1 : 0; x = x < 1 ? 1 : x; }             // :48 saturating_sub(1).max(1)
+        else { x = x > UINT64_MAX - STOCH_ALPHA ? UINT64_MAX : x + STOCH_ALPHA; }   // :50 saturating_add(ALPHA)
+        xl[m] = x;
+        for (int64_t j = f.off[m]; j < f.off[m + 1]; ++j) {                // :54-59
+            total_w[f.var[j]] += x;
+            if (!sat) unsat_w[f.var[j]] += x;
+        }
+        if (!sat) all = false;                                             // :61-63
+    }
+    for (int64_t i = 0; i < f.varnum; ++i) {                               // :67-74
+        if (total_w[i] == 0) continue;   // the reference panics here (gen_range over an empty range): variable in no clause
+        const uint64_t h = stoch_bits(seed, replica, step, (uint64_t)i);
+        const uint64_t r = 1 + (uint64_t)(((unsigned __int128)h * total_w[i]) >> 64);
+        if (r <= unsat_w[i]) v[i] = !v[i];
+    }
+    return all;                                                            // :77
+}
+
+// stoch.rs:80-110 search for R independent replicas: each runs until its own step returns true or `steps` are done
+void stoch_batch(const Formula& f, int64_t R, uint8_t* v, uint64_t* xl, uint64_t seed, int64_t replica_offset,
+                 int64_t steps, int64_t* solved_step) {
+    std::vector<uint64_t> a, b;
+    for (int64_t r = 0; r < R; ++r) {
+        solved_step[r] = -1;
+        for (int64_t s = 0; s < steps; ++s) {                              // :95-99
+            if (stoch_step(f, v + r * f.varnum, xl + r * f.n_clauses, seed, (uint64_t)(replica_offset + r), (uint64_t)s, a, b)) {
+                solved_step[r] = s;
+                break;
+            }
+        }
+    }
+}
 
 extern "C" {
 
@@ -394,5 +448,14 @@ ORACLE_API(float, f32)
 
 double dmm_default_zeta(const void* f) { return double(default_zeta<double>(F(f))); }
 int dmm_evaluate_cnf(const void* f, const uint8_t* assign) { return evaluate_cnf(F(f), assign); }
+
+int dmm_stoch_step(const void* f, uint8_t* v, uint64_t* xl, uint64_t seed, int64_t replica, int64_t step) {
+    std::vector<uint64_t> a, b;
+    return stoch_step(F(f), v, xl, seed, (uint64_t)replica, (uint64_t)step, a, b) ? 1 : 0;
+}
+void dmm_stoch_batch(const void* f, int64_t R, uint8_t* v, uint64_t* xl, uint64_t seed, int64_t replica_offset,
+                     int64_t steps, int64_t* solved_step) {
+    stoch_batch(F(f), R, v, xl, seed, replica_offset, steps, solved_step);
+}
 
 }  // extern "C"

@@ -51,6 +51,10 @@ def _declare(L):
     L.dmm_default_zeta.argtypes = [_P]
     L.dmm_evaluate_cnf.restype = C.c_int
     L.dmm_evaluate_cnf.argtypes = [_P, _P]
+    L.dmm_stoch_step.restype = C.c_int
+    L.dmm_stoch_step.argtypes = [_P, _P, _P, C.c_uint64, _I64, _I64]
+    L.dmm_stoch_batch.restype = None
+    L.dmm_stoch_batch.argtypes = [_P, _I64, _P, _P, C.c_uint64, _I64, _I64, _P]
     for s in ("f64", "f32"):
         f = getattr(L, f"dmm_compute_derivatives_{s}")
         f.restype, f.argtypes = C.c_int, [_P, _P, _P, _P, _D, _P, _P, _P]
@@ -163,6 +167,20 @@ class OracleFormula:
     def evaluate_cnf(self, assign) -> bool:
         a = np.ascontiguousarray(assign, dtype=np.uint8)
         return bool(lib().dmm_evaluate_cnf(self._h, _ptr(a)))
+
+    # --- src/stoch.rs ---------------------------------------------------------------------
+    def stoch_step(self, v, xl, seed: int, replica: int, step: int) -> bool:
+        """stoch.rs:26-78 on v uint8[N] / xl uint64[M] in place; the flip draws are the counter-based stand-in."""
+        assert v.dtype == np.uint8 and xl.dtype == np.uint64
+        return bool(lib().dmm_stoch_step(self._h, _ptr(v), _ptr(xl), seed, replica, step))
+
+    def stoch_batch(self, v, xl, seed: int, steps: int, replica_offset: int = 0) -> np.ndarray:
+        """stoch.rs:80-110 for R replicas (v uint8[R][N], xl uint64[R][M], in place) → first flagged step or -1."""
+        assert v.dtype == np.uint8 and xl.dtype == np.uint64
+        R = v.shape[0]
+        solved = np.full(R, -1, dtype=np.int64)
+        lib().dmm_stoch_batch(self._h, R, _ptr(v), _ptr(xl), seed, replica_offset, steps, _ptr(solved))
+        return solved
 
     # --- batch helpers (CPU baseline) -----------------------------------------------------
     def init_v0(self, seed: int, replica: int, dtype=np.float64) -> np.ndarray:

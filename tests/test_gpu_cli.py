@@ -55,3 +55,33 @@ def test_solve_adaptive_and_usage_errors(golden_dir):
     assert r.returncode == 0 and "satisfies formula: true" in r.stdout
     assert run("batch", "-f", str(golden_dir / "aim100_sat.cnf"), "-b", "4").returncode == 2      # -n is required (main.rs:96)
     assert run("frobnicate").returncode == 2
+
+
+def test_inter_drives_every_visible_gpu_from_one_process(golden_dir):
+    """one handle drives the GPUs of the process; the CLI shards `inter` / `batch` replicas over all visible
+    devices by default (--gpus N to restrict).  The winner does not depend on the device count."""
+    import json
+    from odesat_b200 import _lib as L
+    G = L.lib().odesat_device_count()
+    outs = []
+    for g in sorted({1, G}):
+        r = run("inter", "-f", str(golden_dir / "aim100_sat.cnf"), "-b", "256", "-s", "0.01", "-n", "6000", "--seed", "5",
+                "--gpus", str(g), "--chunk", "64")
+        assert r.returncode == 0, r.stderr
+        assert "Checking if solution vector satisfies formula: true" in r.stdout
+        rec = json.loads(r.stderr.strip().splitlines()[-1])
+        assert rec["gpus"] == g and rec["replicas"] == 256
+        outs.append((rec["steps_run"], [l for l in r.stderr.splitlines() if l.startswith("[odesat_b200]")][0]))
+    assert len(set(outs)) == 1                                   # same steps_run and winner whatever the device count
+    r = run("inter", "-f", str(golden_dir / "aim100_sat.cnf"), "-b", "256", "-s", "0.01", "-n", "6000", "--seed", "5")
+    assert r.returncode == 0 and json.loads(r.stderr.strip().splitlines()[-1])["gpus"] == G      # default: all devices
+    assert run("inter", "-f", str(golden_dir / "aim100_sat.cnf"), "-b", "8", "-s", "0.01", "-n", "10", "--gpus", str(G + 1)).returncode == 1
+
+
+def test_stoch_subcommand(golden_dir):
+    """main.rs:206-252 through the C++ CLI: preprocessing, src/stoch.rs search on the GPU, trace replay, verification."""
+    r = run("stoch", "-f", str(golden_dir / "aim100_sat.cnf"), "-n", "200000", "-b", "32", "--seed", "3")
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    assert lines[:3] == ["Reading CNF formula from file...", "Parsing CNF formula...", "Preprocessing CNF formula..."]
+    assert "Checking if solution vector satisfies formula: true" in lines and "Mapping values..." in lines

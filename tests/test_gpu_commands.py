@@ -57,3 +57,28 @@ def test_inter_driver_script_single_process():
     d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert d["winner"] >= 0 and d["winner_verified_sat"] is True and d["single_gpu_same_winner"] is True
     assert d["flag_step"] < d["steps_run"] <= d["flag_step"] + d["chunk"]
+
+
+@pytest.mark.parametrize("ratio", [None, 3.0])
+def test_stoch_command(golden_dir, tmp_path, ratio):
+    """main.rs:206-252: ratio preprocessing → src/stoch.rs search on the GPU → trace replay → exact verification."""
+    lines = []
+    res = commands.stoch(str(golden_dir / "aim100_sat.cnf"), step_number=200000, ctv_ratio=ratio, batch_size=64, seed=4,
+                         log=lines.append)
+    assert res.is_satisfiable and res.winner >= 0 and res.n_vars < 100
+    assert lines[:3] == ["Reading CNF formula from file...", "Parsing CNF formula...", "Preprocessing CNF formula..."]
+    assert "Checking if solution vector satisfies formula: true" in lines
+    _check_render(res, golden_dir / "aim100_sat.cnf")
+
+
+def test_degenerate_replica_counts(golden_dir):
+    """batch with zero replicas yields the reference's empty map (main.rs:276-308), inter refuses."""
+    res = commands.batch(str(golden_dir / "aim100_sat.cnf"), 10, 0, step_size=0.01, log=lambda s: None)
+    assert not res.is_satisfiable and res.values == {} and res.rendered == ""
+    with pytest.raises(ValueError):
+        commands.inter(str(golden_dir / "aim100_sat.cnf"), 0, step_number=10, step_size=0.01, log=lambda s: None)
+    from odesat_b200 import batch as B
+    from odesat_b200.system import DeviceFormula
+    F = DeviceFormula(cnf.load_dimacs(str(golden_dir / "aim100_sat.cnf")))
+    r = B.simulate_batch(F, 0, seed=1, step_size=0.01, steps=5, precision=L.F32)
+    assert r.winner == -1 and r.steps_run == 0 and not r.assignment.any() and r.solved_step.size == 0
