@@ -58,7 +58,6 @@ template <typename T> struct TileArgs {
     // issued as a PAIR: the STRICT kernel (one step; a no-op when *oor == 0) and the fast kernel (which skips the
     // step the STRICT kernel has taken when *oor != 0) — no device→host flag read in between.
     const unsigned* oor = nullptr;
-    int32_t pf_dist = 3;   // k_tile_fixed_pf: items the L2 prefetch runs ahead of the register loads
 };
 
 constexpr unsigned long long KEY_NONE = 0x7FFFFFFFFFFFFFFFull;   // INT64_MAX: no replica has flagged
@@ -644,180 +643,6 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed_tma(const TileArgs<T> a) {
     }
 }
 
-// ---- L2-prefetched register pipeline (ODESAT_TILE_PIPE=pf) ---------------------------------------------------------
-// Same algorithm and the same items as k_tile_fixed, but the {xs, xl} stream does not pass through shared memory at
-// all: shared memory is the kernel's scarcest resource (the row gathers and the dv read-modify-write already keep
-// the LSU pipe ≈ 75 % busy), and a ring costs one shared-memory write and one read per cell on top of them.
-//   · one thread issues cp.async.bulk.prefetch.L2 for the cells of item i + 1 + pf_dist — no destination register, no
-//     shared memory, no mbarrier: the copy engine pulls the lines from HBM into L2 well ahead of their use;
-//   · every thread loads its cell (LDG.128) and its packed clause (LDG.64) of item i + 1 into registers at the start
-//     of item i — ONE outstanding load pair per thread, so the per-warp scoreboards do not alias (the reason a
-//     deeper register ring never worked, see above) — and the loads hit L2 (≈ 300–600 cycles ≪ one item ≈ 1 300);
-//   · the write-back is the same in-place st.global.cg; a slot is only ever touched by its own thread, so the next
-//     step's load of the slot is ordered after this step's store by program order (ld/st.cg both go to L2).
-// No per-item mbarrier wait, no cross-proxy fence; items may be ragged (EXACT schedule).
-__device__ __forceinline__ uint4 ldg_cg_pinned16(const void* p) {
-    uint4 r;
-    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
-    return r;
-}
-__device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-
-template <typename T, int NT>
-__global__ void __launch_bounds__(NT, 1) k_tile_fixed_pf(const TileArgs<T> a) {
-    constexpr int W = TileTraits<T>::W;
-    using Row = typename TileTraits<T>::Row;
-    using Mem = typename TileTraits<T>::Mem;
-    using IO = RowIO<T, W>;
-    static_assert(sizeof(Mem) == 16, "one 16-byte cell per clause slot");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Row* rows = reinterpret_cast<Row*>(smem_raw);
-    uint2* s_items = reinterpret_cast<uint2*>(smem_raw + (size_t)a.N * sizeof(Row));   // {slot base, count | last << 31}
-
-    const int s_first = launch_first_step<false>(a);   // block-uniform
-    if (s_first >= a.nsteps) return;
-    const unsigned tid = threadIdx.x;
-    const int64_t tile = blockIdx.x;
-    T* vt = a.vt + tile * a.N * W;
-    Mem* tile_mem = a.mem + tile * a.Mpad;
-    Mem* my_mem = tile_mem + tid;                                               // + slot base
-    const uint2* my_entry = reinterpret_cast<const uint2*>(a.entry) + tid;      // + slot base
-    const int n_items = a.n_items;
-
-    for (int i = tid; i < n_items; i += NT) {
-        const uint32_t it = a.items[i];
-        s_items[i] = make_uint2(it & 0xFFFFFu, ((it >> 20) & 0x7FFu) | (it & TILE_ITEM_LAST));
-    }
-    for (int i = tid; i < a.N; i += NT) {
-        T v[W], dv[W];
-#pragma unroll
-        for (int w = 0; w < W; ++w) { v[w] = vt[(int64_t)i * W + w]; dv[w] = T(0); }
-        rows[i] = IO::pack(v, dv);
-    }
-    bool valid[W], frozen[W];
-    int32_t solved_at[W];
-#pragma unroll
-    for (int w = 0; w < W; ++w) {
-        valid[w] = tile * W + w < a.R;
-        solved_at[w] = valid[w] ? a.solved[tile * W + w] : 0;
-        frozen[w] = !valid[w] || (a.freeze && solved_at[w] >= 0);
-    }
-    __syncthreads();
-    // L2 prefetch of one item's cells (≤ 16 KB, contiguous) by ONE thread: the bulk prefetch takes its address and size
-    // from uniform registers (SASS UBLKPF.L2), so per-lane slices would be serialised lane by lane
-    auto prefetch_item = [&](int i) {
-        const uint2 it = s_items[i];
-        const unsigned bytes = (it.y & 0x7FFFFFFFu) * 16u;
-        if (bytes) prefetch_l2_bulk(tile_mem + it.x, bytes);
-    };
-    const int pf = min(max(a.pf_dist, 0), n_items - 1);
-    if (tid == 0) for (int i = 0; i <= pf; ++i) prefetch_item(i);
-    uint2 it_next = s_items[0];
-    uint4 m_next = make_uint4(0u, 0u, 0u, 0u);
-    uint2 e_next = make_uint2(0u, 0u);
-    if (tid < (it_next.y & 0x7FFFFFFFu)) {
-        m_next = ldg_cg_pinned16(at16(my_mem, it_next.x));
-        e_next = ldg_nc_pinned(at8(my_entry, it_next.x));
-    }
-    int i_pf = pf + 1 >= n_items ? pf + 1 - n_items : pf + 1;   // next item to prefetch (wraps into the next step)
-
-    for (int s = s_first; s < a.nsteps; ++s) {
-        bool all_frozen = true;
-#pragma unroll
-        for (int w = 0; w < W; ++w) all_frozen = all_frozen && frozen[w];
-        if (all_frozen) break;
-        bool unsat[W];
-        float mx[2] = {0.0f, 0.0f};
-        T dtw[W];
-#pragma unroll
-        for (int w = 0; w < W; ++w) { unsat[w] = false; dtw[w] = frozen[w] ? T(0) : a.dt; }
-        if constexpr (sizeof(T) == 4) {
-#pragma unroll
-            for (int w = 0; w < W; ++w) asm volatile("" : "+f"(dtw[w]));
-        }
-        for (int i = 0; i < n_items; ++i) {
-            const uint2 it = it_next;
-            const uint4 mraw = m_next;
-            const uint2 e = e_next;
-            {   // registers of the NEXT item (wrapping into the next step), and the L2 prefetch pf_dist items further
-                const int i1 = (i + 1 == n_items) ? 0 : i + 1;
-                it_next = s_items[i1];
-                if (tid < (it_next.y & 0x7FFFFFFFu)) {
-                    m_next = ldg_cg_pinned16(at16(my_mem, it_next.x));
-                    e_next = ldg_nc_pinned(at8(my_entry, it_next.x));
-                }
-                if (tid == 0) prefetch_item(i_pf);
-                i_pf = (i_pf + 1 == n_items) ? 0 : i_pf + 1;
-            }
-            if (tid < (it.y & 0x7FFFFFFFu)) {
-                Mem mm;
-                memcpy(&mm, &mraw, 16);
-                Row* const r0 = reinterpret_cast<Row*>(smem_raw + (e.x & 0x3FFF0u));
-                Row* const r1 = reinterpret_cast<Row*>(smem_raw + ((e.x >> 14) & 0x3FFF0u));
-                Row* const r2 = reinterpret_cast<Row*>(smem_raw + (e.y & 0x3FFF0u));
-                const T q[3] = {(e.y >> 24) & 1u ? T(-1) : T(1), (e.y >> 25) & 1u ? T(-1) : T(1), (e.y >> 26) & 1u ? T(-1) : T(1)};
-                T v[3][W], d[3][W], xs[W], xl[W];
-                IO::unpack(*r0, v[0], d[0]);
-                IO::unpack(*r1, v[1], d[1]);
-                IO::unpack(*r2, v[2], d[2]);
-                IO::unpack_mem(mm, xs, xl);
-                if constexpr (W == 2 && sizeof(T) == 4) {
-                    const float2 v2[3] = {make_float2(v[0][0], v[0][1]), make_float2(v[1][0], v[1][1]), make_float2(v[2][0], v[2][1])};
-                    float2 d2[3] = {make_float2(d[0][0], d[0][1]), make_float2(d[1][0], d[1][1]), make_float2(d[2][0], d[2][1])};
-                    float2 xs2 = make_float2(xs[0], xs[1]), xl2 = make_float2(xl[0], xl[1]);
-                    clause_math_f32x2(v2, d2, q, xs2, xl2, mx, make_float2(dtw[0], dtw[1]), a.xl_max);
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) { d[j][0] = d2[j].x; d[j][1] = d2[j].y; }
-                    xs[0] = xs2.x; xs[1] = xs2.y; xl[0] = xl2.x; xl[1] = xl2.y;
-                } else {
-#pragma unroll
-                    for (int w = 0; w < W; ++w) {
-                        const T vv[3] = {v[0][w], v[1][w], v[2][w]};
-                        T dd[3] = {d[0][w], d[1][w], d[2][w]};
-                        clause_math<T, false>(vv, dd, q, xs[w], xl[w], frozen[w], unsat[w], dtw[w], a.zeta, a.xl_max);
-                        d[0][w] = dd[0]; d[1][w] = dd[1]; d[2][w] = dd[2];
-                    }
-                }
-                IO::store_dv(r0, d[0]);
-                IO::store_dv(r1, d[1]);
-                IO::store_dv(r2, d[2]);
-                __stcg(at16(my_mem, it.x), IO::pack_mem(xs, xl));
-            }
-            if ((int)it.y < 0) __syncthreads();             // last item of a level: block-uniform
-        }
-        if constexpr (W == 2 && sizeof(T) == 4) { unsat[0] = !(mx[0] < 0.5f); unsat[1] = !(mx[1] < 0.5f); }
-        unsigned any_unsat = 0;
-#pragma unroll
-        for (int w = 0; w < W; ++w) any_unsat |= (__syncthreads_or((int)unsat[w]) ? 1u : 0u) << w;
-        for (int i = tid; i < a.N; i += NT) {
-            T v[W], dv[W];
-            IO::unpack(rows[i], v, dv);
-#pragma unroll
-            for (int w = 0; w < W; ++w) { v[w] = euler_clamp(v[w], dv[w], dtw[w], T(-1), T(1)); dv[w] = T(0); }
-            rows[i] = IO::pack(v, dv);
-        }
-#pragma unroll
-        for (int w = 0; w < W; ++w) {
-            if (valid[w] && !frozen[w] && !((any_unsat >> w) & 1u)) {
-                if (solved_at[w] < 0) {
-                    solved_at[w] = a.step0 + s;
-                    if (tid == 0) a.solved[tile * W + w] = solved_at[w];
-                }
-                if (a.freeze) frozen[w] = true;
-            }
-        }
-        __syncthreads();
-    }
-    for (int i = tid; i < a.N; i += NT) {
-        T v[W], dv[W];
-        IO::unpack(rows[i], v, dv);
-#pragma unroll
-        for (int w = 0; w < W; ++w) vt[(int64_t)i * W + w] = v[w];
-    }
-}
-
 // ---- small-instance persistent kernel ---------------------------------------------
 // When every level of the schedule fits in one warp (≤ 32 clauses, e.g. the reference's
 // aim-100 fixtures: N = 100, M = 160) a replica tile is integrated by ONE WARP with the whole
@@ -1148,9 +973,6 @@ template <typename T> struct TileEngine final : TileBase<T> {
     // only pay where an item is a full 768-clause level.  ODESAT_TILE_TMA=0/1 overrides.
     int tma_env = [] { const char* e = std::getenv("ODESAT_TILE_TMA"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
     bool use_tma = false;
-    // {xs, xl} stream as an L2-prefetched register pipeline (k_tile_fixed_pf) instead of a shared-memory ring
-    int pipe_pf = [] { const char* e = std::getenv("ODESAT_TILE_PIPE"); return e ? (std::string(e) == "pf" ? 1 : 0) : -1; }();
-    int pf_dist = [] { const char* e = std::getenv("ODESAT_TILE_PF_DIST"); return e ? std::atoi(e) : 3; }();
     bool small = false;   // one warp per tile, state resident in shared memory (k_tile_small)
     int nt = 512;
     int chunk = 64;   // Euler steps per launch
@@ -1351,16 +1173,8 @@ template <typename T> struct TileEngine final : TileBase<T> {
         k_tile_fixed_tma<T, NT, D><<<(unsigned)tiles, NT, smem, stream>>>(a);
         return true;
     }
-    template <int NT> void launch_pf(TileArgs<T> a) {
-        const size_t smem = (size_t)f.N * 16 + (size_t)(sched->n_items + 2) * 8;
-        static uint64_t attr_devs = 0;
-        ensure_max_smem(k_tile_fixed_pf<T, NT>, (int)kMaxSmem, attr_devs);
-        a.pf_dist = pf_dist;
-        k_tile_fixed_pf<T, NT><<<(unsigned)tiles, NT, smem, stream>>>(a);
-    }
     template <int NT> void launch_d(const TileArgs<T>& a, bool strict) {
         if (strict) { launch<NT, 2, true>(a); return; }
-        if (pipe_pf == 1) { launch_pf<NT>(a); return; }
         if (use_tma) {
             if constexpr (NT == 768 || NT == 512 || NT == 640) {
                 if (depth % 3 == 0 ? launch_tma<NT, 3>(a) : launch_tma<NT, 2>(a)) return;
