@@ -326,16 +326,39 @@ def measure_inter(args, torch, dist, rank, world, local, dev, barrier):
         e1.synchronize()
         return e0.elapsed_time(e1), hit
 
+    def exchange_only(n):
+        """The per-chunk exchange by itself — flag reduction, MIN all-reduce, copy to pinned host, host poll one round
+        late — with no integration in between: its cost per chunk in isolation (a chunk of 32 steps takes 10^4 times
+        longer, so the difference of the two loops above is below their run-to-run noise)."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record()
+            for c in range(n):
+                b.post_key(lo, keys[c & 1].data_ptr())
+                if world > 1:
+                    dist.all_reduce(keys[c & 1][0:1], op=dist.ReduceOp.MIN)
+                host[c & 1].copy_(keys[c & 1], non_blocking=True)
+                evs[c & 1].record()
+                if c >= 1:
+                    evs[(c - 1) & 1].synchronize()
+            e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1) / n * 1e3
+
     loop(warm_chunks, True)
     barrier()
     ms_c, hit = loop(chunks, True)
     barrier()
     ms_n, _ = loop(chunks, False)
     barrier()
-    t = torch.tensor([ms_c, ms_n], dtype=torch.float64, device=dev)
+    exchange_only(20)
+    barrier()
+    us_x = exchange_only(200)
+    barrier()
+    t = torch.tensor([ms_c, ms_n, us_x], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_c, ms_n = float(t[0]), float(t[1])
+    ms_c, ms_n, us_x = float(t[0]), float(t[1]), float(t[2])
     eng = {L.ENGINE_GATHER: "gather", L.ENGINE_TILE: "tile"}[b.engine]
     # the pinned block and the events were used on the batch's stream: release them while that stream still exists
     del host, keys, evs, t
@@ -353,8 +376,12 @@ def measure_inter(args, torch, dist, rank, world, local, dev, barrier):
                              else "none at 1 GPU: the key goes device -> pinned host",
                        "in_timed_region": True, "per_run": chunks, "bytes": 8,
                        "ms_per_step_without": ms_n / steps,
-                       "cost_us_per_chunk": (ms_c - ms_n) / chunks * 1e3,
-                       "cost_fraction": (ms_c - ms_n) / ms_c},
+                       "difference_us_per_chunk": (ms_c - ms_n) / chunks * 1e3,
+                       "exchange_alone_us_per_chunk": us_x,
+                       "cost_fraction": us_x * 1e-3 * chunks / ms_c,
+                       "note": "difference = the same chunks with and without the collective (below run-to-run noise); "
+                               "exchange_alone = 200 back-to-back rounds of flag reduction + all-reduce + pinned copy + "
+                               "one-round-late host poll, max over ranks; cost_fraction = exchange_alone x chunks / timed region"},
         "roofline_frac": bytes_step * steps / (ms_c * 1e-3) / 1e9 / peak,
     }
 

@@ -96,7 +96,7 @@ typedef struct odesat_params {
                             kernels read the previous key on the device and do nothing once it is set.        */
     int32_t sub_batches; /* shards per device with their own stream, so that the host→device copy of one
                             shard's initial state overlaps the integration of the previous one; <= 0 → auto
-                            (4 when v0 comes from the host and a device gets >= 2048 replicas, else 1)       */
+                            (one per 512 replicas of a device, at most 8, when v0 comes from the host; else 1) */
 } odesat_params;
 
 typedef struct odesat_formula odesat_formula;   /* device-resident CSR + variable→clause transpose */

@@ -77,6 +77,10 @@ struct BatchBase {
     virtual int preferred_chunk() const { return 32; }   // Euler steps between early-exit polls when the caller does not say
     virtual void verify(uint8_t* out) = 0;
     virtual void assignment(int64_t r, uint8_t* out) = 0;
+    // flags + exact verification of every replica with ONE synchronisation: enqueue (verify kernel, copies into pinned
+    // host staging), then — after the other shards have enqueued theirs — collect
+    virtual void results_enqueue() = 0;
+    virtual void results_collect(int64_t* solved_out, uint8_t* verified_out) = 0;
     virtual void get_dt(double* out) = 0;
     virtual void set_dt(const double* in) = 0;
     // single-state helpers (R == 1 mirrors of odesat::system)
@@ -108,6 +112,9 @@ template <typename T> struct BatchImpl final : BatchBase {
     DevBuf<T> staging;
     DevBuf<uint8_t> small8;
     DevBuf<double> dscratch;
+    DevBuf<uint32_t> bad_buf;   // [R] verification result (some clause falsified)
+    int32_t* h_solved = nullptr;   // pinned staging of results_enqueue / results_collect
+    uint32_t* h_bad = nullptr;
     StateBuf<T> Snap;           // snapshot of the gather-engine state
     DevBuf<int32_t> solved_snap;
     int64_t step_snap = 0;
@@ -695,6 +702,46 @@ template <typename T> struct BatchImpl final : BatchBase {
         int64_t k = 0;
         wait_key(2, &k, nullptr);
         return k;
+    }
+
+    ~BatchImpl() override {
+        if (h_solved) cudaFreeHost(h_solved);
+        if (h_bad) cudaFreeHost(h_bad);
+    }
+    // bad_buf[r] = replica r's thresholded state falsifies some clause (enqueue only)
+    void verify_enqueue() {
+        if (!bad_buf.p) bad_buf.alloc((size_t)std::max<int64_t>(R, 1), &dev_bytes);
+        ODESAT_CUDA(cudaMemsetAsync(bad_buf.p, 0, bad_buf.bytes(), stream));
+        bool done = false;
+        if (tile && tile->has_direct() && !canon_ahead && !canon_current && f->M > 0) {
+            const int64_t n = tile->verify_direct(bad_buf.p);   // on the tile layout: no export
+            launches += n;
+            done = n > 0;
+        }
+        if (!done) tile_to_canon();
+        StateBuf<T>& s = canon();
+        if (f->M > 0 && !done) {
+            dim3 g, b;
+            geom(f->M, g, b);
+            k_verify<T><<<g, b, 0, stream>>>(f->dev, s.v.p, R, Rp, bad_buf.p);
+            ++launches;
+        }
+        ODESAT_CUDA(cudaGetLastError());
+    }
+    void results_enqueue() override {
+        if (R == 0) return;
+        if (!h_solved) {
+            ODESAT_CUDA(cudaHostAlloc((void**)&h_solved, (size_t)R * 4, cudaHostAllocDefault));
+            ODESAT_CUDA(cudaHostAlloc((void**)&h_bad, (size_t)R * 4, cudaHostAllocDefault));
+        }
+        verify_enqueue();
+        ODESAT_CUDA(cudaMemcpyAsync(h_solved, solved.p, (size_t)R * 4, cudaMemcpyDeviceToHost, stream));
+        ODESAT_CUDA(cudaMemcpyAsync(h_bad, bad_buf.p, (size_t)R * 4, cudaMemcpyDeviceToHost, stream));
+    }
+    void results_collect(int64_t* solved_out, uint8_t* verified_out) override {
+        if (R == 0) return;
+        sync();
+        for (int64_t r = 0; r < R; ++r) { solved_out[r] = h_solved[r]; verified_out[r] = h_bad[r] ? 0 : 1; }
     }
 
     void verify(uint8_t* out) override {

@@ -316,7 +316,9 @@ void simulate_batch_impl(const odesat_formula* f, int64_t R, TH* v, TH* xs, TH* 
     G = (int)std::min<int64_t>(G, R);
     int sub = p->sub_batches;
     if (const char* e = std::getenv("ODESAT_SUB_BATCHES")) sub = std::atoi(e);
-    if (sub <= 0) sub = (v != nullptr && r.fixed && R / G >= 2048) ? 4 : 1;
+    // measured on B200 (4096 replicas, N = 10 000, 20 steps per call): 14.9 / 13.4 / 12.9 / 12.6 / 13.3 ms for 1 / 2 / 4 / 8 /
+    // 16 sub-batches against 11.2 ms of pure integration → about 512 replicas per sub-batch, at most 8
+    if (sub <= 0) sub = (v != nullptr && r.fixed) ? (int)std::max<int64_t>(1, std::min<int64_t>(8, R / G / 512)) : 1;
     if (inter_adaptive) sub = 1;
     sub = (int)std::max<int64_t>(1, std::min<int64_t>(sub, R / G));
     std::vector<Shard> sh = plan_shards(f, R, G, sub);
@@ -346,11 +348,8 @@ void simulate_batch_impl(const odesat_formula* f, int64_t R, TH* v, TH* xs, TH* 
         dr = drive(sh, r, mode, lockstep, prepare);
     }
     std::vector<uint8_t> ver((size_t)R, 0);
-    for (Shard& s : sh) {
-        DeviceGuard g(s.dev);
-        s.b->status(solved.data() + s.off, nullptr);
-        s.b->verify(ver.data() + s.off);                                         // cnf.rs:246-264
-    }
+    for (Shard& s : sh) { DeviceGuard g(s.dev); s.b->results_enqueue(); }       // cnf.rs:246-264 on every shard, then
+    for (Shard& s : sh) { DeviceGuard g(s.dev); s.b->results_collect(solved.data() + s.off, ver.data() + s.off); }   // one sync each
     int64_t win = -1, src = 0;
     if (mode == ODESAT_MODE_BATCH) {
         for (int64_t q = 0; q < R; ++q) if (ver[q]) { win = q; break; }          // main.rs:305-307

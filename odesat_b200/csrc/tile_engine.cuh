@@ -1178,6 +1178,8 @@ template <typename T> struct TileEngine final : TileBase<T> {
         if (use_tma) {
             if constexpr (NT == 768 || NT == 512 || NT == 640) {
                 if (depth % 3 == 0 ? launch_tma<NT, 3>(a) : launch_tma<NT, 2>(a)) return;
+            } else if constexpr (NT == 1024) {
+                if (launch_tma<NT, 2>(a)) return;
             }
         }   // ring of 2 divides every schedule padding
         switch (depth) {
