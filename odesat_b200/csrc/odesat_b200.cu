@@ -620,8 +620,7 @@ int odesat_tile_schedule_stats(int64_t varnum, int64_t n_clauses, const int64_t*
         f.build(varnum, n_clauses, clause_off, lits);
         ODESAT_REQUIRE(f.K == 3 && f.distinct_vars, "tile schedules need uniform 3-literal clauses with distinct variables");
         // the same level construction the tile engine uses for a CTA of `threads` threads
-        const int target = threads >= 512 ? threads : 1024;
-        auto lv = schedule == ODESAT_SCHED_EXACT ? build_tile_levels(f, schedule, threads) : build_tile_levels(f, schedule, target, target / 2);
+        auto lv = schedule == ODESAT_SCHED_EXACT ? build_tile_levels(f, schedule, threads) : build_balanced_levels(f, threads, tile_items_per_level());
         auto s = build_tile_schedule(f, *lv, schedule, threads, depth, /*upload=*/false);
         out[0] = s->nlev;
         out[1] = s->n_items;

@@ -643,6 +643,10 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed_tma(const TileArgs<T> a) {
     }
 }
 
+}  // namespace odesat
+#include "tile_ws.cuh"
+namespace odesat {
+
 // ---- small-instance persistent kernel ---------------------------------------------
 // When every level of the schedule fits in one warp (≤ 32 clauses, e.g. the reference's
 // aim-100 fixtures: N = 100, M = 160) a replica tile is integrated by ONE WARP with the whole
@@ -973,6 +977,16 @@ template <typename T> struct TileEngine final : TileBase<T> {
     // only pay where an item is a full 768-clause level.  ODESAT_TILE_TMA=0/1 overrides.
     int tma_env = [] { const char* e = std::getenv("ODESAT_TILE_TMA"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
     bool use_tma = false;
+    // warp-specialised persistent kernel (tile_ws.cuh): producer warp + full/empty mbarriers, barriers only between
+    // levels, work queue of (sub-chunk, tile).  ODESAT_TILE_WS=0/1 overrides.
+    int ws_env = [] { const char* e = std::getenv("ODESAT_TILE_WS"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
+    // items per BALANCED level: 1 = one CTA width of clauses per level (a barrier after every item), 0 = wide levels,
+    // as few colours as the maximum variable degree allows (tile_schedule.hpp).  ODESAT_TILE_IPL overrides.
+    int ipl = tile_items_per_level();
+    int ksub_env = [] { const char* e = std::getenv("ODESAT_TILE_KSUB"); return e ? std::atoi(e) : 0; }();
+    bool use_ws = false;
+    int num_sms = 148;
+    DevBuf<int> work;     // [1 + tiles] work-queue counter and per-tile published sub-chunks (k_tile_ws)
     bool small = false;   // one warp per tile, state resident in shared memory (k_tile_small)
     int nt = 512;
     int chunk = 64;   // Euler steps per launch
@@ -1009,13 +1023,14 @@ template <typename T> struct TileEngine final : TileBase<T> {
         // levels: BALANCED colour classes do not depend on the CTA width; EXACT levels are list-scheduled
         // with the CTA width as the cap (one item per level), so they are built per candidate width
         auto levels_for = [&](int cap) {
-            const int key = kind + 2 * cap;
+            const int wide = (kind == ODESAT_SCHED_BALANCED && cap >= 512 && ipl != 1) ? 1 + ipl : 0;
+            const int key = kind + 2 * cap + 4096 * wide;
             auto it = f.tile_levels.find(key);
             if (it == f.tile_levels.end()) {
-                // BALANCED: colour classes of one item (a CTA width of clauses), capacity rounded to half an item
-                const int target = cap >= 512 ? cap : 1024;
+                // BALANCED: colour classes of one item (a CTA width of clauses), capacity rounded to half an item —
+                // or, wide, of several whole items
                 it = f.tile_levels.emplace(key, kind == ODESAT_SCHED_EXACT ? build_tile_levels(f, kind, cap)
-                                                                           : build_tile_levels(f, kind, target, target / 2)).first;
+                                                                           : build_balanced_levels(f, cap, ipl)).first;
             }
             return it->second;
         };
@@ -1077,18 +1092,30 @@ template <typename T> struct TileEngine final : TileBase<T> {
         depth = pick_depth(f.N, nt, (int)(f.M / nt + 3 * (int64_t)lv->bucket.size() + 16));
         if (depth < 2) throw Error(ODESAT_EUNSUPPORTED, "variables do not fit in shared memory");
         if (want >= 2 && want <= depth) depth = want;
-        const int key = (kind * 64 + nt / 32) * 16 + depth;
+        const int wide = (kind == ODESAT_SCHED_BALANCED && nt >= 512 && ipl != 1) ? 1 + ipl : 0;
+        const int key = ((kind * 64 + nt / 32) * 16 + depth) + 65536 * wide;
         auto it = f.tile_sched.find(key);
         if (it == f.tile_sched.end()) it = f.tile_sched.emplace(key, build_tile_schedule(f, *lv, kind, nt, depth)).first;
         sched = it->second;
         if (smem_bytes(f.N, sched->n_items, nt, depth) > kMaxSmem) throw Error(ODESAT_EUNSUPPORTED, "schedule does not fit in shared memory");
         use_tma = tma_env >= 0 ? tma_env == 1 : (kind == ODESAT_SCHED_BALANCED && nt == 768 && depth % 3 == 0);
+        // measured (B200, headline size, ms/step): f32 0.5315 against 0.5444 for the TMA kernel on the same wide levels and
+        // 0.5554 for round 1's kernel and levels; f64 0.614 against 0.582 (TMA, wide) — so f64 keeps the TMA kernel
+        use_ws = ws_env >= 0 ? ws_env == 1 : (kind == ODESAT_SCHED_BALANCED && nt == 768 && depth % 3 == 0 && sizeof(T) == 4);
         {   // the TMA kernel orders a slot's write-back against its next bulk read with a proxy fence issued at the start
-            // of the next NON-EMPTY item: at least one such item must lie between the write and the wrap-around refill
+            // of the next NON-EMPTY item: at least one such item must lie between the write and the wrap-around refill.
+            // The warp-specialised kernel gates the re-read of a slot on the consumption of the stage's PREVIOUS item,
+            // which must be a different, later item than the one that wrote the slot: every stage needs two real items.
             int real = 0;
             for (uint32_t it : sched->items) real += ((it >> 20) & 0x7FFu) != 0u;
-            if (real < 2 * depth + 2) use_tma = false;
+            if (real < 2 * depth + 2) use_tma = use_ws = false;
         }
+        {
+            int dev = 0;
+            ODESAT_CUDA(cudaGetDevice(&dev));
+            ODESAT_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        }
+        if (use_ws) work.alloc((size_t)tiles + 1, ledger);
         vt.alloc((size_t)(tiles * f.N * W), ledger);
         mem.alloc((size_t)(tiles * sched->Mpad), ledger);
         oor.alloc(1, ledger);
@@ -1173,8 +1200,44 @@ template <typename T> struct TileEngine final : TileBase<T> {
         k_tile_fixed_tma<T, NT, D><<<(unsigned)tiles, NT, smem, stream>>>(a);
         return true;
     }
+    // Steps per sub-chunk of the work queue: the launch's k steps of `tiles` tiles are dealt to G persistent CTAs in
+    // rounds of ksub steps; a round costs ksub steps plus the reload of the tile's rows and the refill of the ring
+    // (measured: ≈ 0.25 of a step at the headline size).  Many tiles per SM → one sub-chunk (the whole launch).
+    int pick_ksub(int k) const {
+        if (ksub_env > 0) return std::min(ksub_env, k);
+        const int64_t G = std::max(1, num_sms);
+        int best = k;
+        double best_cost = 1e300;
+        for (int ks = k; ks >= 1; --ks) {
+            const int64_t nsub = (k + ks - 1) / ks;
+            const double cost = (double)((tiles * nsub + G - 1) / G) * ((double)ks + 0.25);
+            if (cost < best_cost * 0.995) { best_cost = cost; best = ks; }
+        }
+        return best;
+    }
+    template <int NT, int D> bool launch_ws(const TileArgs<T>& a) {
+        const size_t smem = (size_t)f.N * 16 + (size_t)NT * D * 24 + (size_t)(sched->n_items + 2) * 8 + (size_t)D * 16 + 16;
+        if (smem > kMaxSmem || sched->n_items % D != 0 || !work.p || tiles > (1 << 24)) return false;
+        static uint64_t attr_devs = 0;
+        ensure_max_smem(k_tile_ws<T, NT, D>, (int)kMaxSmem, attr_devs);
+        TileWork wk;
+        wk.counter = work.p;
+        wk.done = work.p + 1;
+        wk.tiles = (int)tiles;
+        wk.ksub = pick_ksub(a.nsteps);
+        wk.nsub = (a.nsteps + wk.ksub - 1) / wk.ksub;
+        ODESAT_CUDA(cudaMemsetAsync(work.p, 0, ((size_t)tiles + 1) * sizeof(int), stream));
+        const int64_t grid = std::min<int64_t>(tiles * wk.nsub, num_sms);
+        k_tile_ws<T, NT, D><<<(unsigned)grid, NT + 32, smem, stream>>>(a, wk);
+        return true;
+    }
     template <int NT> void launch_d(const TileArgs<T>& a, bool strict) {
         if (strict) { launch<NT, 2, true>(a); return; }
+        if (use_ws) {
+            if constexpr (NT == 768 || NT == 512) {
+                if (depth % 3 == 0 ? launch_ws<NT, 3>(a) : launch_ws<NT, 2>(a)) return;
+            }
+        }
         if (use_tma) {
             if constexpr (NT == 768 || NT == 512 || NT == 640) {
                 if (depth % 3 == 0 ? launch_tma<NT, 3>(a) : launch_tma<NT, 2>(a)) return;

@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <array>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <numeric>
 #include <queue>
@@ -180,8 +181,9 @@ struct TileLevels {
 
 // BALANCED: `target` = clauses per level aimed for, `round` = the item width the class capacity is
 // rounded up to (a level is a whole number of items wherever possible).
+// `ipl` != 1 (BALANCED): wide levels of `ipl` items of `target` clauses each (0 = as many as the degree bound allows).
 // EXACT: `target` = cap on the clauses of a level (<= 0: none).
-inline std::shared_ptr<TileLevels> build_tile_levels(const odesat_formula& f, int kind, int target = 1024, int round = 512) {
+inline std::shared_ptr<TileLevels> build_tile_levels(const odesat_formula& f, int kind, int target = 1024, int round = 512, int ipl = 1) {
     auto s = std::make_shared<TileLevels>();
     const int64_t M = f.M, N = f.N;
     std::vector<int32_t> level(M, 0);
@@ -228,18 +230,10 @@ inline std::shared_ptr<TileLevels> build_tile_levels(const odesat_formula& f, in
             ++nlev;
         }
     } else {
-        // target: levels of 1024 clauses (a whole number of 512-thread items), but never fewer
-        // colours than the max variable degree; classes are capped at a multiple of 512
-        int C = (int)std::max<int64_t>(f.max_degree + 2, (M + target - 1) / target);
-        const int cap = (int)(((M + C - 1) / C + round - 1) / round * round);
-
-        std::vector<std::vector<uint64_t>> usedc;   // per variable: bitset of colours taken
-        int words = (C + 63 + 64) / 64;             // slack for overflow colours
-        std::vector<uint64_t> bits((size_t)N * words, 0);
-        std::vector<int32_t> load((size_t)words * 64, 0);
+        // Greedy least-loaded colouring with C colours of capacity `cap`, most constrained clauses first; colours
+        // are added when a clause fits nowhere.  → number of colours used.
         std::vector<int32_t> order(M);
         std::iota(order.begin(), order.end(), 0);
-        // most constrained first: clauses whose variables have the highest degree
         std::vector<int32_t> deg(N);
         for (int64_t i = 0; i < N; ++i) deg[i] = f.h_voff[i + 1] - f.h_voff[i];
         std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
@@ -247,30 +241,78 @@ inline std::shared_ptr<TileLevels> build_tile_levels(const odesat_formula& f, in
             const int db = deg[var_of(b, 0)] + deg[var_of(b, 1)] + deg[var_of(b, 2)];
             return da > db;
         });
-        int ncol = C;
-        for (int32_t m : order) {
-            const uint64_t* b0 = &bits[(size_t)var_of(m, 0) * words];
-            const uint64_t* b1 = &bits[(size_t)var_of(m, 1) * words];
-            const uint64_t* b2 = &bits[(size_t)var_of(m, 2) * words];
-            int best = -1, bl = INT32_MAX;
-            for (int c = 0; c < ncol; ++c) {
-                const uint64_t forb = b0[c >> 6] | b1[c >> 6] | b2[c >> 6];
-                if (!((forb >> (c & 63)) & 1) && load[c] < bl && load[c] < cap) { best = c; bl = load[c]; }
+        auto colour = [&](int C, int cap, std::vector<int32_t>& lvl) {
+            const int words = (C + 63 + 64) / 64;             // slack for overflow colours
+            std::vector<uint64_t> bits((size_t)N * words, 0);
+            std::vector<int32_t> load((size_t)words * 64, 0);
+            int ncol = C;
+            for (int32_t m : order) {
+                const uint64_t* b0 = &bits[(size_t)var_of(m, 0) * words];
+                const uint64_t* b1 = &bits[(size_t)var_of(m, 1) * words];
+                const uint64_t* b2 = &bits[(size_t)var_of(m, 2) * words];
+                int best = -1, bl = INT32_MAX;
+                for (int c = 0; c < ncol; ++c) {
+                    const uint64_t forb = b0[c >> 6] | b1[c >> 6] | b2[c >> 6];
+                    if (!((forb >> (c & 63)) & 1) && load[c] < bl && load[c] < cap) { best = c; bl = load[c]; }
+                }
+                if (best < 0) {
+                    if (ncol >= words * 64) throw Error(ODESAT_EINVAL, "balanced schedule ran out of colours");
+                    best = ncol++;
+                }
+                lvl[m] = best;
+                load[best]++;
+                for (int j = 0; j < 3; ++j) bits[(size_t)var_of(m, j) * words + (best >> 6)] |= 1ull << (best & 63);
             }
-            if (best < 0) {
-                if (ncol >= words * 64) throw Error(ODESAT_EINVAL, "balanced schedule ran out of colours");
-                best = ncol++;
+            return ncol;
+        };
+        if (ipl == 1) {
+            // one item per level: levels of `target` clauses, but never fewer colours than the max variable degree
+            // (+ 2 of slack for the greedy); classes are capped at a multiple of `round`
+            const int C = (int)std::max<int64_t>(f.max_degree + 2, (M + target - 1) / target);
+            const int cap = (int)(((M + C - 1) / C + round - 1) / round * round);
+            nlev = colour(C, cap, level);
+        } else {
+            // WIDE levels (kernels whose ring does not need a barrier after every item): a level is `k` items of
+            // `target` clauses, and the colour count goes down to its lower bound, the maximum variable degree —
+            // half the level barriers at the headline size (28 levels of 2 × 768 instead of 56 of 768).  k = 0: as
+            // many items per level as that bound allows.  The greedy has no slack at C·cap ≈ M, so C, C + 1, C + 2
+            // are tried and the one with the fewest items (then levels) is kept.
+            const int64_t md = std::max<int64_t>(1, f.max_degree);
+            const int64_t k = ipl > 0 ? ipl : std::max<int64_t>(1, (M + (int64_t)target * md - 1) / ((int64_t)target * md));
+            const int C0 = (int)std::max<int64_t>(md, (M + k * target - 1) / (k * target));
+            int64_t best_items = INT64_MAX;
+            int best_lev = 0;
+            std::vector<int32_t> lvl(M, 0);
+            for (int C = C0; C <= C0 + 2; ++C) {
+                const int nc = colour(C, (int)(k * target), lvl);
+                std::vector<int32_t> cnt(nc, 0);
+                for (int64_t m = 0; m < M; ++m) cnt[lvl[m]]++;
+                int64_t items = 0;
+                int lev = 0;
+                for (int c : cnt) { items += (c + target - 1) / target; lev += c > 0; }
+                if (items < best_items || (items == best_items && lev < best_lev)) {
+                    best_items = items; best_lev = lev; level = lvl; nlev = nc;
+                }
             }
-            level[m] = best;
-            load[best]++;
-            for (int j = 0; j < 3; ++j) bits[(size_t)var_of(m, j) * words + (best >> 6)] |= 1ull << (best & 63);
         }
-        nlev = ncol;
     }
     s->nlev = nlev;
     s->bucket.assign(nlev, {});
     for (int64_t m = 0; m < M; ++m) s->bucket[level[m]].push_back((int32_t)m);
     return s;
+}
+
+// Items per BALANCED level the tile engine compiles for: 1 = one CTA width of clauses per level (a barrier after every
+// item), 0 (default) = wide levels, as few colours as the maximum variable degree allows.  ODESAT_TILE_IPL overrides.
+inline int tile_items_per_level() {
+    const char* e = std::getenv("ODESAT_TILE_IPL");
+    return e ? std::max(0, std::atoi(e)) : 0;
+}
+// The BALANCED levels of a CTA of `cap` threads, as the tile engine builds them.
+inline std::shared_ptr<TileLevels> build_balanced_levels(const odesat_formula& f, int cap, int ipl) {
+    const int target = cap >= 512 ? cap : 1024;
+    return (cap >= 512 && ipl != 1) ? build_tile_levels(f, ODESAT_SCHED_BALANCED, target, target, ipl)
+                                    : build_tile_levels(f, ODESAT_SCHED_BALANCED, target, target / 2);
 }
 
 // `depth`: prefetch ring depth of the kernel the schedule is for; the item list is padded with

@@ -262,3 +262,64 @@ def test_tma_ring_soak_4096_replicas_1024_steps(monkeypatch):
     for a, c in zip(out["1"], out["0"]):
         assert eq(a, c)
     assert (np.abs(out["1"][0]) == 1).mean() > 0.02
+
+
+@pytest.mark.parametrize("prec", [L.F32, L.F64])
+def test_warp_specialised_kernel_equals_the_per_thread_ring(monkeypatch, prec):
+    """k_tile_ws (producer warp + full/empty mbarriers, barriers only between the wide BALANCED levels, persistent CTAs
+    with a (sub-chunk, tile) work queue) walks the same schedule as the per-thread cp.async kernel: bit-identical
+    states, whatever the sub-chunk size (1 step: every step of a tile may run on another SM; 3: ragged last
+    sub-chunk; 0: automatic), across the 64-step launch chunk."""
+    f = cnf.random_ksat(10_000, 4.3, seed=20240613)
+    D = S.DeviceFormula(f)
+    dtype = B.np_dtype(prec)
+    F = O.OracleFormula(f.varnum, f.clause_off, f.lits)
+    R = 331                                                       # odd: the last tile is half empty (f32)
+    v, xs, xl = F.init_batch(3, R, dtype)
+    out = {}
+    for name, ws, ksub in (("ring", "0", "0"), ("ws", "1", "0"), ("ws1", "1", "1"), ("ws3", "1", "3")):
+        monkeypatch.setenv("ODESAT_TILE_WS", ws)
+        monkeypatch.setenv("ODESAT_TILE_TMA", "0")
+        monkeypatch.setenv("ODESAT_TILE_KSUB", ksub)
+        b = B.ReplicaBatch(D, R, prec, L.ENGINE_TILE, L.SCHED_BALANCED)
+        b.upload(v, xs, xl)
+        b.run_fixed(0.01, 0.001, 1, freeze=False)
+        first = b.download()
+        b.run_fixed(0.01, 0.001, 69, freeze=False)
+        out[name] = first + b.download()
+        b.close()
+    for name in ("ws", "ws1", "ws3"):
+        for a, c in zip(out[name], out["ring"]):
+            assert eq(a, c), name
+    o = [v.copy(), xs.copy(), xl.copy()]
+    F.batch_fixed(*o, 0.01, 0.001, 1, freeze=False, nthreads=O.host_cores())
+    tol = dict(rtol=1e-5, atol=1e-6) if prec == L.F32 else dict(rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(out["ws"][0], o[0], **tol)
+    assert eq(out["ws"][1], o[1]) and eq(out["ws"][2], o[2])
+
+
+def test_warp_specialised_kernel_flags_and_freezes_like_the_ring(monkeypatch):
+    """Replicas that flag are frozen (system.rs:149-153 then dt = 0) and their flag steps recorded — also when a tile's
+    sub-chunks run on different SMs, and when a whole tile is frozen (its work items become no-ops)."""
+    f = cnf.random_ksat(4000, 3.0, seed=5)                        # flags between steps ~340 and ~450 at dt = 0.1
+    D = S.DeviceFormula(f)
+    F = O.OracleFormula(f.varnum, f.clause_off, f.lits)
+    R = 301
+    v, xs, xl = F.init_batch(11, R, np.float32)
+    out = {}
+    for name, ws, ksub in (("ring", "0", "0"), ("ws", "1", "0"), ("ws2", "1", "2")):
+        monkeypatch.setenv("ODESAT_TILE_WS", ws)
+        monkeypatch.setenv("ODESAT_TILE_TMA", "0")
+        monkeypatch.setenv("ODESAT_TILE_NT", "512")
+        monkeypatch.setenv("ODESAT_TILE_KSUB", ksub)
+        b = B.ReplicaBatch(D, R, L.F32, L.ENGINE_TILE, L.SCHED_BALANCED)
+        b.upload(v, xs, xl)
+        b.run_fixed(0.1, 0.001, 400, freeze=True)
+        st, _ = b.status()
+        out[name] = (st,) + b.download()
+        b.close()
+    nflag = int((out["ring"][0] >= 0).sum())
+    assert R // 8 < nflag                                          # replicas do flag on this instance
+    for name in ("ws", "ws2"):
+        for a, c in zip(out[name], out["ring"]):
+            assert eq(a, c), name

@@ -125,3 +125,26 @@ def test_exact_levels_are_list_scheduled_to_the_cta_width(threads):
         for v in var[m]:
             assert last_level.get(v, -1) < level_of[m]
             last_level[v] = level_of[m]
+
+
+@pytest.mark.parametrize("ipl", ["1", "0"])
+def test_wide_balanced_levels_at_the_bench_size(monkeypatch, ipl):
+    """BALANCED levels of the benched formula for 768-thread CTAs: one item per level (56 levels, the round-1 form) or
+    WIDE levels — as many colours as the maximum variable degree (28), two full 768-clause items each, so half the
+    level barriers for the same 56 items.  Either way no variable occurs twice inside a level."""
+    monkeypatch.setenv("ODESAT_TILE_IPL", ipl)
+    f = cnf.random_ksat(10_000, 4.3, seed=20240611 + 2)
+    var = (np.abs(f.lits) - 1).reshape(-1, 3)
+    nlev, items, perm, wf = compile_schedule(f, L.SCHED_BALANCED, 768, 3)
+    levels = levels_of(items, perm)
+    assert sorted(perm[perm >= 0]) == list(range(f.n_clauses))
+    for lv in levels:
+        vs = var[lv].reshape(-1)
+        assert len(np.unique(vs)) == len(vs)
+    real = sum(1 for it in items if ((int(it) >> 20) & 0x7FF) > 0)
+    max_degree = int(np.bincount(var.reshape(-1)).max())
+    if ipl == "1":
+        assert nlev == real == 56
+    else:
+        assert nlev == max_degree == 28 and real == 56
+    assert len(items) % 6 == 0 and 1.0 <= wf < 1.6
