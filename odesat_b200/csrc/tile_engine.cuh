@@ -1034,7 +1034,7 @@ template <typename T> struct TileEngine final : TileBase<T> {
             }
             return it->second;
         };
-        static const int cand[] = {128, 512, 640, 768, 1024};
+        static const int cand[] = {128, 512, 640, 704, 768, 1024};
         if (const char* e = std::getenv("ODESAT_TILE_CHUNK")) { const int v = std::atoi(e); if (v > 0) chunk = v; }
         std::shared_ptr<TileLevels> lv;
         {   // small-instance mode: every level fits in a warp and the whole tile state fits in shared memory
@@ -1074,6 +1074,12 @@ template <typename T> struct TileEngine final : TileBase<T> {
             double best = 1e300;
             for (int c : cand) {
                 if (forced && c != forced) continue;
+                // 704 threads exist for one case: f32 BALANCED where a ring of FOUR stages then fits beside the rows
+                // (N = 10 000: 160 KB + 4 x 16.5 KB), which the warp-specialised kernel turns into 2 % (measured
+                // in one run: 0.5302 ms/step against 0.5417 at 768 threads with a ring of three; ncu showed the
+                // consumers of the 768-thread kernel waiting 1.5 cycles per issued instruction for ring data)
+                if (c == 704 && !forced && !(sizeof(T) == 4 && kind == ODESAT_SCHED_BALANCED && ws_env != 0 &&
+                                              pick_depth(f.N, 704, (int)(f.M / 704 + 256)) == 4)) continue;
                 if (pick_depth(f.N, c, (int)(f.M / c + 256)) < 2 && c != 128) continue;   // its ring would not fit
                 auto l = levels_for(c);
                 double items = 0;
@@ -1081,7 +1087,7 @@ template <typename T> struct TileEngine final : TileBase<T> {
                 // width preference measured on B200 at the headline size (BALANCED, ms/step at 512/640/768/1024 threads:
                 // f32 0.611/0.596/0.588/0.603, f64 0.656/0.637/0.659/0.666): the widest CTA is not the fastest
                 // (with the TMA-fed ring, BALANCED f64 is fastest at 768 threads too: 0.600 ms against 0.629 at 640 with cp.async)
-                const double pref = c == 1024 ? (sizeof(T) == 4 ? 1.12 : 1.25) : (c == 768 && sizeof(T) == 8 && kind == ODESAT_SCHED_EXACT ? 1.10 : 1.0);
+                const double pref = c == 1024 ? (sizeof(T) == 4 ? 1.12 : 1.25) : (c == 768 && sizeof(T) == 8 && kind == ODESAT_SCHED_EXACT ? 1.10 : (c == 704 ? 0.93 : 1.0));
                 const double cost = items * (454.0 + c) * pref;
                 if (cost < best) { best = cost; nt = c; lv = l; }
             }
@@ -1101,7 +1107,7 @@ template <typename T> struct TileEngine final : TileBase<T> {
         use_tma = tma_env >= 0 ? tma_env == 1 : (kind == ODESAT_SCHED_BALANCED && nt == 768 && depth % 3 == 0);
         // measured (B200, headline size, ms/step): f32 0.5315 against 0.5444 for the TMA kernel on the same wide levels and
         // 0.5554 for round 1's kernel and levels; f64 0.614 against 0.582 (TMA, wide) — so f64 keeps the TMA kernel
-        use_ws = ws_env >= 0 ? ws_env == 1 : (kind == ODESAT_SCHED_BALANCED && nt == 768 && depth % 3 == 0 && sizeof(T) == 4);
+        use_ws = ws_env >= 0 ? ws_env == 1 : (kind == ODESAT_SCHED_BALANCED && ((nt == 768 && depth % 3 == 0) || (nt == 704 && depth == 4)) && sizeof(T) == 4);
         {   // the TMA kernel orders a slot's write-back against its next bulk read with a proxy fence issued at the start
             // of the next NON-EMPTY item: at least one such item must lie between the write and the wrap-around refill.
             // The warp-specialised kernel gates the re-read of a slot on the consumption of the stage's PREVIOUS item,
@@ -1215,6 +1221,7 @@ template <typename T> struct TileEngine final : TileBase<T> {
         }
         return best;
     }
+    int ws_early = [] { const char* e = std::getenv("ODESAT_TILE_WS_EARLY"); return e ? std::atoi(e) : 0; }();
     template <int NT, int D> bool launch_ws(const TileArgs<T>& a) {
         const size_t smem = (size_t)f.N * 16 + (size_t)NT * D * 24 + (size_t)(sched->n_items + 2) * 8 + (size_t)D * 16 + 16;
         if (smem > kMaxSmem || sched->n_items % D != 0 || !work.p || tiles > (1 << 24)) return false;
@@ -1226,6 +1233,7 @@ template <typename T> struct TileEngine final : TileBase<T> {
         wk.tiles = (int)tiles;
         wk.ksub = pick_ksub(a.nsteps);
         wk.nsub = (a.nsteps + wk.ksub - 1) / wk.ksub;
+        wk.early = ws_early;
         ODESAT_CUDA(cudaMemsetAsync(work.p, 0, ((size_t)tiles + 1) * sizeof(int), stream));
         const int64_t grid = std::min<int64_t>(tiles * wk.nsub, num_sms);
         k_tile_ws<T, NT, D><<<(unsigned)grid, NT + 32, smem, stream>>>(a, wk);
@@ -1264,6 +1272,12 @@ template <typename T> struct TileEngine final : TileBase<T> {
         else if (nt == 512) launch_d<512>(a, strict);
         else if (nt == 640) launch_d<640>(a, strict);
         else if (nt == 768) launch_d<768>(a, strict);
+        else if (nt == 704) {   // ring of 4 beside the rows of 10 000 variables (experiment): warp-specialised kernel or the per-thread ring
+            if (strict) launch<704, 2, true>(a);
+            else if (!(use_ws && depth == 4 && launch_ws<704, 4>(a))) {
+                if (depth >= 4) launch<704, 4, false>(a); else launch<704, 2, false>(a);
+            }
+        }
         else launch_d<1024>(a, strict);
     }
 

@@ -278,7 +278,17 @@ inline std::shared_ptr<TileLevels> build_tile_levels(const odesat_formula& f, in
             // many items per level as that bound allows.  The greedy has no slack at C·cap ≈ M, so C, C + 1, C + 2
             // are tried and the one with the fewest items (then levels) is kept.
             const int64_t md = std::max<int64_t>(1, f.max_degree);
-            const int64_t k = ipl > 0 ? ipl : std::max<int64_t>(1, (M + (int64_t)target * md - 1) / ((int64_t)target * md));
+            // k = 0: the k whose colour count max(md, ceil(M / (k·target))) gives the fewest items (then the fewest levels)
+            int64_t k = ipl;
+            if (k <= 0) {
+                int64_t best_it = INT64_MAX;
+                for (int64_t kk = 1; kk <= 4; ++kk) {
+                    const int64_t Ck = std::max<int64_t>(md, (M + kk * target - 1) / (kk * target));
+                    const int64_t load = (M + Ck - 1) / Ck;
+                    const int64_t it = Ck * ((load + target - 1) / target);
+                    if (it < best_it || (it == best_it && Ck < std::max<int64_t>(md, (M + k * target - 1) / (k * target)))) { best_it = it; k = kk; }
+                }
+            }
             const int C0 = (int)std::max<int64_t>(md, (M + k * target - 1) / (k * target));
             int64_t best_items = INT64_MAX;
             int best_lev = 0;

@@ -34,10 +34,16 @@ struct TileWork {
     int tiles = 0;
     int nsub = 1;             // sub-chunks per launch
     int ksub = 0;             // steps per sub-chunk
+    int early = 0;            // 1: a warp releases its ring stage as soon as its cells are in registers (not at the end of the item)
 };
 
 __device__ __forceinline__ void mbar_arrive(void* bar) {
     asm volatile("{\n.reg .b64 t;\nmbarrier.arrive.shared::cta.b64 t, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrive that the compiler may schedule freely but not before `dep0` / `dep1` (the values loaded from the stage) exist:
+// no memory clobber, so it does not pin the surrounding loads and stores the way a plain asm volatile("..." ::: "memory") does
+__device__ __forceinline__ void mbar_arrive_after(void* bar, unsigned dep0, unsigned dep1) {
+    asm volatile("{\n.reg .b64 t;\n.reg .b32 u;\nand.b32 u, %1, %2;\nmbarrier.arrive.shared::cta.b64 t, [%0];\n}" ::"r"(smem_u32(bar)), "r"(dep0), "r"(dep1));
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -186,6 +192,9 @@ __global__ void __launch_bounds__(NT + 32, 1) k_tile_ws(const TileArgs<T> a, con
                             if (mine) {
                                 const Mem mm = ring_m[k * NT + tid];
                                 const uint2 e = ring_e[k * NT + tid];
+                                // (a warp is converged here: items are full except the last of a level, whose partial warp
+                                // releases late)
+                                if (wk.early && lane == 0 && cnt == NT) mbar_arrive_after(empty + k, e.y, *reinterpret_cast<const unsigned*>(&mm));
                                 r0 = reinterpret_cast<Row*>(smem_raw + (e.x & 0x3FFF0u));
                                 r1 = reinterpret_cast<Row*>(smem_raw + ((e.x >> 14) & 0x3FFF0u));
                                 r2 = reinterpret_cast<Row*>(smem_raw + (e.y & 0x3FFF0u));
@@ -221,8 +230,10 @@ __global__ void __launch_bounds__(NT + 32, 1) k_tile_ws(const TileArgs<T> a, con
                             }
                             // the warp's cells and clause words have long been consumed (the stores above depend on them):
                             // release the stage to the producer
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(empty + k);
+                            if (!(wk.early && cnt == NT)) {
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(empty + k);
+                            }
                             if ((int)it.y < 0) named_bar_sync(1, NT);     // last item of a level: the level's dv stores are complete
                         }
                     }
