@@ -359,7 +359,7 @@ def measure_inter(args, torch, dist, rank, world, local, dev, barrier):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_c, ms_n, us_x = float(t[0]), float(t[1]), float(t[2])
-    eng = {L.ENGINE_GATHER: "gather", L.ENGINE_TILE: "tile"}[b.engine]
+    eng = {L.ENGINE_GATHER: "gather", L.ENGINE_TILE: "tile", L.ENGINE_SLAB: "slab"}[b.engine]
     # the pinned block and the events were used on the batch's stream: release them while that stream still exists
     del host, keys, evs, t
     torch.cuda.synchronize()
@@ -413,7 +413,7 @@ def run_gpu(args):
     f, name = workload(args)
     prec = L.F32 if args.precision == "f32" else L.F64
     P = 4 if prec == L.F32 else 8
-    engine = {"auto": L.ENGINE_AUTO, "gather": L.ENGINE_GATHER, "tile": L.ENGINE_TILE}[args.engine]
+    engine = {"auto": L.ENGINE_AUTO, "gather": L.ENGINE_GATHER, "tile": L.ENGINE_TILE, "slab": L.ENGINE_SLAB}[args.engine]
     sched = L.SCHED_EXACT if args.schedule == "exact" else L.SCHED_BALANCED
     F = DeviceFormula(f)
     zeta = f.default_zeta()
@@ -451,7 +451,7 @@ def run_gpu(args):
         barrier()
         n_launch = b.launches - l0
         st, _ = b.status()
-        eng = {L.ENGINE_GATHER: "gather", L.ENGINE_TILE: "tile"}[b.engine]
+        eng = {L.ENGINE_GATHER: "gather", L.ENGINE_TILE: "tile", L.ENGINE_SLAB: "slab"}[b.engine]
         b.close()
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
@@ -585,7 +585,7 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong (default, BASELINE configs[2]): --replicas in total, sharded 1/2/4/8; weak: --replicas per GPU")
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
-    ap.add_argument("--engine", default="auto", choices=["auto", "gather", "tile"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "gather", "tile", "slab"])
     ap.add_argument("--schedule", default="balanced", choices=["exact", "balanced"],
                     help="tile-engine clause schedule: balanced = throughput mode (dv summed in colour order, "
                          "agrees with the reference to rounding); exact = the reference's summation order, bit-identical")

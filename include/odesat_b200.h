@@ -58,8 +58,14 @@ typedef enum odesat_precision { ODESAT_F64 = 0, ODESAT_F32 = 1 } odesat_precisio
  *          streamed in conflict-free levels.  Larger instances can be forced onto a thread-block
  *          cluster (rows in distributed shared memory) by requesting TILE explicitly; AUTO does
  *          not, because the general engine is faster there.
+ *  SLAB  : throughput path for fixed steps on uniform 3-literal formulas that do NOT fit in shared memory (up to
+ *          2^20 variables): the gather engine's deterministic two-phase RHS (bit-identical sums) run by ONE
+ *          persistent kernel per chunk of steps over slabs of 32 bytes of replicas, ordered so that a slab's
+ *          per-literal contributions are consumed while they are still in L2 (csrc/slab_engine.cuh).
+ *          Experimental: bit-identical, HBM traffic 13 GB per step against the gather engine's 22.7 GB at N = 50 000,
+ *          but latency-bound and slower (4.8 ms against 3.56 ms per step), so AUTO never picks it.
  *  AUTO  : TILE when it applies and the batch has at least 8 replicas, else GATHER. */
-typedef enum odesat_engine { ODESAT_ENGINE_AUTO = 0, ODESAT_ENGINE_GATHER = 1, ODESAT_ENGINE_TILE = 2 } odesat_engine;
+typedef enum odesat_engine { ODESAT_ENGINE_AUTO = 0, ODESAT_ENGINE_GATHER = 1, ODESAT_ENGINE_TILE = 2, ODESAT_ENGINE_SLAB = 3 } odesat_engine;
 
 /* Clause schedule of the TILE engine.
  *  EXACT   : order-preserving levels (list scheduling) — each variable receives its clause

@@ -6,7 +6,7 @@ device-resident replica batches and the one-process-per-GPU sharding layer; `cnf
 formula plumbing (DIMACS reader, normaliser, random k-SAT generator).
 """
 from . import _lib  # noqa: F401
-from ._lib import (ENGINE_AUTO, ENGINE_GATHER, ENGINE_TILE, F32, F64, MODE_BATCH, MODE_INTER, SCHED_BALANCED,  # noqa: F401
+from ._lib import (ENGINE_AUTO, ENGINE_GATHER, ENGINE_SLAB, ENGINE_TILE, F32, F64, MODE_BATCH, MODE_INTER, SCHED_BALANCED,  # noqa: F401
                    SCHED_EXACT, OdesatError)
 
 __all__ = ["_lib", "cnf", "system", "batch", "OdesatError"]

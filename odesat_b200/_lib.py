@@ -15,7 +15,7 @@ SO_PATH = Path(os.environ.get("ODESAT_B200_SO", str(_HERE / "csrc" / "libodesat_
 
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, 1, 2, 3, 4
 F64, F32 = 0, 1
-ENGINE_AUTO, ENGINE_GATHER, ENGINE_TILE = 0, 1, 2
+ENGINE_AUTO, ENGINE_GATHER, ENGINE_TILE, ENGINE_SLAB = 0, 1, 2, 3
 SCHED_EXACT, SCHED_BALANCED = 0, 1
 MODE_BATCH, MODE_INTER = 0, 1
 INT64_MAX = (1 << 63) - 1

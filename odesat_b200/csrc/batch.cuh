@@ -10,6 +10,7 @@
 #include "kernels_small.cuh"
 #include "tile_cluster.cuh"
 #include "tile_engine.cuh"
+#include "slab_engine.cuh"
 
 #ifndef ODESAT_CLAUSE_HALF_VEC
 #define ODESAT_CLAUSE_HALF_VEC 0   // measured on B200: half-width clause vectors lose (9.8 vs 8.4 ms at N = 50k)
@@ -152,6 +153,12 @@ template <typename T> struct BatchImpl final : BatchBase {
                                                                  : (want_tile && ctile_ok && force_c);
         const bool use_tile = want_tile && tile_ok && !use_ctile;
         engine = (use_tile || use_ctile) ? ODESAT_ENGINE_TILE : ODESAT_ENGINE_GATHER;
+        // SLAB: formulas too large for shared memory, batches with enough replicas to fill the GPU with 32-byte slabs
+        std::string why_s;
+        const bool slab_ok = SlabEngine<T>::supports(*f, R, &why_s);
+        if (engine_ == ODESAT_ENGINE_SLAB && !slab_ok) throw Error(ODESAT_EUNSUPPORTED, "slab engine cannot run this formula: " + why_s);
+        if (engine_ == ODESAT_ENGINE_SLAB || (engine_ == ODESAT_ENGINE_AUTO && engine == ODESAT_ENGINE_GATHER && slab_ok && SlabEngine<T>::preferred(*f, R)))
+            engine = ODESAT_ENGINE_SLAB;
         const int64_t N = f->N, M = f->M;
         solved.alloc((size_t)std::max<int64_t>(Rp, 1), &dev_bytes);
         dtv.alloc((size_t)std::max<int64_t>(Rp, 1), &dev_bytes);
@@ -171,7 +178,8 @@ template <typename T> struct BatchImpl final : BatchBase {
                 if (!tile) engine = ODESAT_ENGINE_GATHER;
             }
         }
-        if (engine != ODESAT_ENGINE_TILE) {
+        if (engine == ODESAT_ENGINE_SLAB) tile.reset(new SlabEngine<T>(*f, R, stream, &dev_bytes));
+        if (!tile) {
             S[0].alloc(N, M, Rp, &dev_bytes);   // S[1] (derivatives / adaptive ping-pong) on first use
             pick_slab();
             unsat.alloc((size_t)std::max<int64_t>(Rp, 1), &dev_bytes);

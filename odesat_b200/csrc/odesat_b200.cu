@@ -42,7 +42,7 @@ BatchBase* make_batch(const odesat_formula* f, int64_t R, int precision, int eng
     ODESAT_REQUIRE(f != nullptr, "formula is NULL");
     ODESAT_REQUIRE(R >= 0, "negative replica count");
     ODESAT_REQUIRE(precision == ODESAT_F64 || precision == ODESAT_F32, "unknown precision");
-    ODESAT_REQUIRE(engine >= ODESAT_ENGINE_AUTO && engine <= ODESAT_ENGINE_TILE, "unknown engine");
+    ODESAT_REQUIRE(engine >= ODESAT_ENGINE_AUTO && engine <= ODESAT_ENGINE_SLAB, "unknown engine");
     ODESAT_REQUIRE(schedule == ODESAT_SCHED_EXACT || schedule == ODESAT_SCHED_BALANCED, "unknown schedule");
     require_device();
     int dev = 0;

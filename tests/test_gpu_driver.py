@@ -33,7 +33,7 @@ def easy_instance():
 
 
 @pytest.mark.parametrize("chunk", [0, 7, 1])
-@pytest.mark.parametrize("engine", [L.ENGINE_TILE, L.ENGINE_GATHER])
+@pytest.mark.parametrize("engine", [L.ENGINE_TILE, L.ENGINE_GATHER, L.ENGINE_SLAB])
 def test_inter_write_back_is_lock_step_for_every_chunk(engine, chunk):
     """system.rs:279-293: when the loop stops, EVERY replica has taken exactly `steps` Euler steps — also when the
     device polls only every `chunk` steps (the overshoot of the non-winners)."""
@@ -66,7 +66,7 @@ def test_simulate_inter_entry_point_default_chunk_is_lock_step():
         assert eq(states[r].v, v[r]) and eq(states[r].xs, xs[r]) and eq(states[r].xl, xl[r])
 
 
-@pytest.mark.parametrize("engine", [L.ENGINE_TILE, L.ENGINE_GATHER])
+@pytest.mark.parametrize("engine", [L.ENGINE_TILE, L.ENGINE_GATHER, L.ENGINE_SLAB])
 @pytest.mark.parametrize("chunk", [3, 32])
 def test_speculative_chunks_keep_winner_steps_and_flags(engine, chunk):
     """Without write-back the next chunk is already enqueued when the host reads a chunk's key; its kernels see the key

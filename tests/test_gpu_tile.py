@@ -280,6 +280,7 @@ def test_warp_specialised_kernel_equals_the_per_thread_ring(monkeypatch, prec):
     for name, ws, ksub in (("ring", "0", "0"), ("ws", "1", "0"), ("ws1", "1", "1"), ("ws3", "1", "3")):
         monkeypatch.setenv("ODESAT_TILE_WS", ws)
         monkeypatch.setenv("ODESAT_TILE_TMA", "0")
+        monkeypatch.setenv("ODESAT_TILE_NT", "704")              # same CTA width, hence the same schedule, for both kernels
         monkeypatch.setenv("ODESAT_TILE_KSUB", ksub)
         b = B.ReplicaBatch(D, R, prec, L.ENGINE_TILE, L.SCHED_BALANCED)
         b.upload(v, xs, xl)
