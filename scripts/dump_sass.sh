@@ -1,5 +1,5 @@
 #!/bin/bash
-# Dumps the SASS of the dominant kernel (the one bench.py times: k_tile_fixed_tma<float, 768, 3>) from the built
+# Dumps the SASS of the dominant kernel (the one bench.py times: k_tile_ws<float, 704, 4>) from the built
 # library, with the counts of the mnemonics that identify a hand-written Blackwell kernel:
 #   UBLKCP            cp.async.bulk (TMA bulk copy, global -> shared)
 #   SYNCS             mbarrier arrive / expect_tx / try_wait
@@ -8,7 +8,7 @@
 # Usage: scripts/dump_sass.sh [function-substring] > profiles/rNN_tile_tma_sass.txt
 set -euo pipefail
 SO="$(dirname "$0")/../odesat_b200/csrc/libodesat_b200.so"
-FN="${1:-_ZN6odesat16k_tile_fixed_tmaIfLi768ELi3EEEvNS_8TileArgsIT_EE}"
+FN="${1:-_ZN6odesat9k_tile_wsIfLi704ELi4EEEvNS_8TileArgsIT_EENS_8TileWorkE}"
 TMP="$(mktemp)"
 cuobjdump -sass -fun "$FN" "$SO" > "$TMP"
 echo "# cuobjdump -sass -fun $FN libodesat_b200.so   ($(date -u +%Y-%m-%dT%H:%MZ), nvcc $(nvcc --version | grep -o 'release [0-9.]*'))"
