@@ -382,6 +382,7 @@ template <typename T> struct BatchImpl final : BatchBase {
         a.zeta = (T)zeta;
         a.fast = (v_in_range && std::isfinite(zeta)) ? 1 : 0;
         if (const char* e = std::getenv("ODESAT_GATHER_FAST")) { if (e[0] == '0') a.fast = 0; }
+        if (const char* e = std::getenv("ODESAT_GATHER_PACKED")) { if (e[0] == '0' && a.fast) a.fast = 2; }   // 2: scalar fast path (A/B)
         if (const char* e = std::getenv("ODESAT_GATHER_L2HINTS")) a.l2_hints = std::atoi(e);
         a.xl_max = T(1e4) * T(f->M);
         a.solved_step = solved.p;

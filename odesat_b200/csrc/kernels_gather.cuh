@@ -18,6 +18,7 @@
 // per literal: 15 state words per clause instead of 5).  FIXED steps update the state in place.
 #pragma once
 #include "common.cuh"
+#include "packed_f32x2.cuh"
 
 namespace odesat {
 
@@ -390,6 +391,44 @@ __global__ void __launch_bounds__(256) k_clause_stream(const GatherArgs<T> a) {
         }
         xs_m = *reinterpret_cast<const RVec<T, V>*>(cell(r, 3));
         xl_m = *reinterpret_cast<const RVec<T, V>*>(cell(r, 4));
+        if constexpr (MODE == G_FIXED && sizeof(T) == 4 && V == 4) {
+            // Fixed step, f32, four replicas per thread, fast domain: the tile kernel's arithmetic for two PAIRS of
+            // replicas (packed f32x2: half the instructions of the scalar fast path below; the kernel was issue-bound
+            // once the v gathers hit L2).  Same operations per lane, so the same bits.  A skipped replica (frozen, or
+            // padding beyond R) integrates with dt = 0: its memories are already inside their clamp ranges.
+            if (a.fast == 1) {
+                const float q3[3] = {qs[0], qs[1], qs[2]};
+                RVec<T, V> t[3], o1, o2;
+                float mxv[4];
+#pragma unroll
+                for (int k = 0; k < 4; k += 2) {
+                    const float2 v2[3] = {make_float2(vis[0].x[k], vis[0].x[k + 1]), make_float2(vis[1].x[k], vis[1].x[k + 1]),
+                                          make_float2(vis[2].x[k], vis[2].x[k + 1])};
+                    float2 d2[3] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
+                    float2 xs2 = make_float2(xs_m.x[k], xs_m.x[k + 1]), xl2 = make_float2(xl_m.x[k], xl_m.x[k + 1]);
+                    float mxk[2] = {0.0f, 0.0f};
+                    const float2 dt2 = make_float2(skip[k] ? 0.0f : dt[k], skip[k + 1] ? 0.0f : dt[k + 1]);
+                    clause_math_f32x2(v2, d2, q3, xs2, xl2, mxk, dt2, a.xl_max);
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) { t[j].x[k] = d2[j].x; t[j].x[k + 1] = d2[j].y; }
+                    o1.x[k] = skip[k] ? xs_m.x[k] : xs2.x; o1.x[k + 1] = skip[k + 1] ? xs_m.x[k + 1] : xs2.y;
+                    o2.x[k] = skip[k] ? xl_m.x[k] : xl2.x; o2.x[k + 1] = skip[k + 1] ? xl_m.x[k + 1] : xl2.y;
+                    mxv[k] = mxk[0]; mxv[k + 1] = mxk[1];
+                }
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    if (a.l2_hints) vstore_cs<T, V>(a.contrib + (mrow[r] * 3 + j) * a.cstride + (rep - a.rep0), t[j]);
+                    else vstore<T, V>(a.contrib + (mrow[r] * 3 + j) * a.cstride + (rep - a.rep0), t[j]);
+                }
+                // system.rs:88 — C_m >= 0.25 ⇔ min >= 0.5 exactly (C_m = 0.5·min, a power-of-two scaling)
+#pragma unroll
+                for (int u = 0; u < V; ++u)
+                    if (!skip[u] && !(mxv[u] < 0.5f) && a.unsat[rep + u] == 0u) a.unsat[rep + u] = 1u;
+                if (a.l2_hints) { vstore_cs<T, V>(a.oxs + at, o1); vstore_cs<T, V>(a.oxl + at, o2); }
+                else { vstore<T, V>(a.oxs + at, o1); vstore<T, V>(a.oxl + at, o2); }
+                continue;
+            }
+        }
         T mn[V], sm[V], c[V];
         if (a.fast) {
             // Fast arithmetic (see clause_math in tile_engine.cuh): 1 − q·v as one exact FMA, min / second-min as a
