@@ -195,6 +195,27 @@ __device__ __forceinline__ uint2 ldg_nc_pinned(const uint2* p) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Work queue of the persistent kernels (k_tile_ws in tile_ws.cuh; k_tile_fixed when wk.counter != nullptr): work items
+// are (sub-chunk of steps, tile) in sub-chunk-major order; see tile_ws.cuh.
+struct TileWork {
+    int* counter = nullptr;   // next work item (zeroed by the host before the launch)
+    int* done = nullptr;      // [tiles] sub-chunks of the tile that are published (zeroed before the launch)
+    int tiles = 0;
+    int nsub = 1;             // sub-chunks per launch
+    int ksub = 0;             // steps per sub-chunk
+    int early = 0;            // 1: a warp releases its ring stage as soon as its cells are in registers (not at the end of the item)
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+
 // One fused fixed Euler step per loop iteration, `nsteps` per launch; one CTA per replica tile.
 //
 // Work decomposition: the schedule is a sequence of ITEMS, each up to NT consecutive clause
@@ -215,8 +236,12 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // ER (entry-in-ring): the packed clause word travels through the cp.async ring too (24-byte
 // cells) instead of the 1-ahead register load.  Better when an item is short (narrow CTA): one
 // item time does not always cover an L2 round trip.
-template <typename T, int NT, int D, bool STRICT, bool ER>
-__global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
+// QUEUED = false: one CTA per tile, the whole launch (round 1; compiled without the work loop — wrapping the same code in
+// a run-time loop cost the EXACT schedule 4.5 %: 0.645 → 0.675 ms/step).  QUEUED = true: the CTAs are persistent and take
+// (sub-chunk, tile) work items from the queue like k_tile_ws, so that a shard with few tiles per SM (strong scaling)
+// has no tail wave; the ring is re-primed per work item.
+template <typename T, int NT, int D, bool STRICT, bool ER, bool QUEUED>
+__global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a, const TileWork wk) {
     constexpr int W = TileTraits<T>::W;
     using Row = typename TileTraits<T>::Row;
     using Mem = typename TileTraits<T>::Mem;
@@ -230,22 +255,40 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
     const int s_first = launch_first_step<STRICT>(a);   // block-uniform
     if (s_first >= a.nsteps) return;
     const unsigned tid = threadIdx.x;
-    const int64_t tile = blockIdx.x;
-    T* vt = a.vt + tile * a.N * W;
-    Mem* my_mem = a.mem + tile * a.Mpad + tid;                                  // + slot base
     const uint2* my_entry = reinterpret_cast<const uint2*>(a.entry) + tid;      // + slot base
     Mem* my_cell_m = ring_m + tid;                                              // + k·NT
     uint2* my_cell_e = ring_e + tid;
     const int n_items = a.n_items;
+    __shared__ int s_work;
 
     for (int i = tid; i < n_items; i += NT) {
         const uint32_t it = a.items[i];
         s_items[i] = make_uint2(it & 0xFFFFFu, ((it >> 20) & 0x7FFu) | (it & TILE_ITEM_LAST));
     }
+    constexpr bool queued = QUEUED;
+    for (int round = 0; QUEUED || round == 0; ++round) {
+    int sub = 0, sa = s_first, sb = a.nsteps;
+    int64_t tile = blockIdx.x;
+    if constexpr (QUEUED) {
+        __syncthreads();
+        if (tid == 0) s_work = atomicAdd(wk.counter, 1);
+        __syncthreads();
+        const int widx = s_work;
+        if (widx >= wk.tiles * wk.nsub) break;
+        sub = widx / wk.tiles;
+        tile = widx - sub * wk.tiles;
+        sa = s_first + sub * wk.ksub;
+        sb = min(a.nsteps, sa + wk.ksub);
+        if (sub > 0 && tid == 0) { while (ld_acquire_gpu(wk.done + tile) < sub) { } }
+        __syncthreads();
+    }
+    if (sa < sb) {
+    T* vt = a.vt + tile * a.N * W;
+    Mem* my_mem = a.mem + tile * a.Mpad + tid;                                  // + slot base
     for (int i = tid; i < a.N; i += NT) {
         T v[W], dv[W];
 #pragma unroll
-        for (int w = 0; w < W; ++w) { v[w] = vt[(int64_t)i * W + w]; dv[w] = T(0); }
+        for (int w = 0; w < W; ++w) { v[w] = QUEUED ? __ldcg(vt + (int64_t)i * W + w) : vt[(int64_t)i * W + w]; dv[w] = T(0); }
         rows[i] = IO::pack(v, dv);
     }
     bool valid[W], frozen[W];
@@ -253,7 +296,7 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
 #pragma unroll
     for (int w = 0; w < W; ++w) {
         valid[w] = tile * W + w < a.R;
-        solved_at[w] = valid[w] ? a.solved[tile * W + w] : 0;
+        solved_at[w] = valid[w] ? (QUEUED ? __ldcg(a.solved + tile * W + w) : a.solved[tile * W + w]) : 0;
         frozen[w] = !valid[w] || (a.freeze && solved_at[w] >= 0);
     }
     __syncthreads();
@@ -270,7 +313,7 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
     uint2 e_next = make_uint2(0u, 0u);
     if (!ER && tid < (it_next.y & 0x7FFFFFFFu)) e_next = __ldg(at8(my_entry, it_next.x));
 
-    for (int s = s_first; s < a.nsteps; ++s) {
+    for (int s = sa; s < sb; ++s) {
         bool all_frozen = true;
 #pragma unroll
         for (int w = 0; w < W; ++w) all_frozen = all_frozen && frozen[w];
@@ -370,7 +413,7 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
                 // the pre-update state of this step was all-satisfied (system.rs:149-153)
                 if (solved_at[w] < 0) {
                     solved_at[w] = a.step0 + s;
-                    if (tid == 0) a.solved[tile * W + w] = solved_at[w];
+                    if (tid == 0) { if (QUEUED) __stcg(a.solved + tile * W + w, solved_at[w]); else a.solved[tile * W + w] = solved_at[w]; }
                 }
                 if (a.freeze) frozen[w] = true;
             }
@@ -382,8 +425,17 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed(const TileArgs<T> a) {
         T v[W], dv[W];
         IO::unpack(rows[i], v, dv);
 #pragma unroll
-        for (int w = 0; w < W; ++w) vt[(int64_t)i * W + w] = v[w];
+        for (int w = 0; w < W; ++w) { if (QUEUED) __stcg(vt + (int64_t)i * W + w, v[w]); else vt[(int64_t)i * W + w] = v[w]; }
     }
+    }   // sa < sb
+    if constexpr (QUEUED) {
+        if (wk.nsub > 1) {
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) st_release_gpu(wk.done + tile, sub + 1);
+        }
+    }
+    }   // work items
 }
 
 // ---- TMA-fed variant (ODESAT_TILE_TMA=1) -----------------------------------------------------------------------
@@ -915,6 +967,11 @@ template <typename T> struct TileEngine final : TileBase<T> {
     int ipl = tile_items_per_level();
     int ksub_env = [] { const char* e = std::getenv("ODESAT_TILE_KSUB"); return e ? std::atoi(e) : 0; }();
     bool use_ws = false;
+    // the per-thread-ring kernel (EXACT, and every fallback) can take work from the same queue when that removes a tail
+    // wave.  Measured on B200 (EXACT, 256 tiles on 148 SMs, 20 steps): f64 0.1033 → 0.0982 ms/step, f32 0.0951 → 0.0982
+    // (the queued instantiation's code is ≈ 4.5 % slower per step, which eats the f32 gain) — default: f64 only.
+    // ODESAT_TILE_QUEUE=0/1 overrides.
+    bool queue_fixed = [] { const char* e = std::getenv("ODESAT_TILE_QUEUE"); return e ? e[0] != '0' : sizeof(T) == 8; }();
     int num_sms = 148;
     DevBuf<int> work;     // [1 + tiles] work-queue counter and per-tile published sub-chunks (k_tile_ws)
     bool small = false;   // one warp per tile, state resident in shared memory (k_tile_small)
@@ -1051,7 +1108,7 @@ template <typename T> struct TileEngine final : TileBase<T> {
             ODESAT_CUDA(cudaGetDevice(&dev));
             ODESAT_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
         }
-        if (use_ws) work.alloc((size_t)tiles + 1, ledger);
+        work.alloc((size_t)tiles + 1, ledger);
         vt.alloc((size_t)(tiles * f.N * W), ledger);
         mem.alloc((size_t)(tiles * sched->Mpad), ledger);
         oor.alloc(1, ledger);
@@ -1124,9 +1181,26 @@ template <typename T> struct TileEngine final : TileBase<T> {
 
     template <int NT, int D, bool STRICT> void launch(const TileArgs<T>& a) {
         const size_t smem = smem_bytes(f.N, sched->n_items, NT, D);
+        // persistent CTAs + work queue when the one-CTA-per-tile grid would leave a tail wave worth cutting
+        if constexpr (!STRICT && (NT == 512 || NT == 640 || NT == 768)) {
+            if (queue_fixed && work.p && tiles <= (1 << 24) && a.nsteps > 1) {
+                const int ks = pick_ksub(a.nsteps);
+                if (ks < a.nsteps || ksub_env > 0) {
+                    static uint64_t attr_q = 0;
+                    ensure_max_smem(k_tile_fixed<T, NT, D, false, true, true>, (int)kMaxSmem, attr_q);
+                    TileWork wk;
+                    wk.counter = work.p; wk.done = work.p + 1; wk.tiles = (int)tiles; wk.ksub = ks;
+                    wk.nsub = (a.nsteps + ks - 1) / ks;
+                    ODESAT_CUDA(cudaMemsetAsync(work.p, 0, ((size_t)tiles + 1) * sizeof(int), stream));
+                    const int64_t grid = std::min<int64_t>(tiles * wk.nsub, num_sms);
+                    k_tile_fixed<T, NT, D, false, true, true><<<(unsigned)grid, NT, smem, stream>>>(a, wk);
+                    return;
+                }
+            }
+        }
         static uint64_t attr_devs = 0;   // per instantiation: devices on which the attribute is set
-        ensure_max_smem(k_tile_fixed<T, NT, D, STRICT, (NT < 1024)>, (int)kMaxSmem, attr_devs);
-        k_tile_fixed<T, NT, D, STRICT, (NT < 1024)><<<(unsigned)tiles, NT, smem, stream>>>(a);
+        ensure_max_smem(k_tile_fixed<T, NT, D, STRICT, (NT < 1024), false>, (int)kMaxSmem, attr_devs);
+        k_tile_fixed<T, NT, D, STRICT, (NT < 1024), false><<<(unsigned)tiles, NT, smem, stream>>>(a, TileWork());
     }
     template <int NT, int D> bool launch_tma(const TileArgs<T>& a) {
         const size_t smem = (size_t)f.N * 16 + (size_t)NT * D * 24 + (size_t)(sched->n_items + 2) * 8 + (size_t)D * 8;

@@ -28,15 +28,6 @@
 
 namespace odesat {
 
-struct TileWork {
-    int* counter = nullptr;   // next work item (zeroed by the host before the launch)
-    int* done = nullptr;      // [tiles] sub-chunks of the tile that are published (zeroed before the launch)
-    int tiles = 0;
-    int nsub = 1;             // sub-chunks per launch
-    int ksub = 0;             // steps per sub-chunk
-    int early = 0;            // 1: a warp releases its ring stage as soon as its cells are in registers (not at the end of the item)
-};
-
 __device__ __forceinline__ void mbar_arrive(void* bar) {
     asm volatile("{\n.reg .b64 t;\nmbarrier.arrive.shared::cta.b64 t, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -48,15 +39,6 @@ __device__ __forceinline__ void mbar_arrive_after(void* bar, unsigned dep0, unsi
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_gpu(int* p, int v) {
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 // Shared memory: rows[N] (16 B) | ring_m[D][NT] (16 B) | ring_e[D][NT] (8 B) | items[n_items + 2] (8 B)
 //                | full[D], empty[D] mbarriers | work word
 // Measured on B200 (headline size, f32, ms per step): releasing the stage at the END of the item 0.5395; releasing it

@@ -324,3 +324,60 @@ def test_warp_specialised_kernel_flags_and_freezes_like_the_ring(monkeypatch):
     for name in ("ws", "ws2"):
         for a, c in zip(out[name], out["ring"]):
             assert eq(a, c), name
+
+
+def test_steps_to_flag_distribution_of_the_benched_kernel(monkeypatch):
+    """north_star: "the distribution of steps-to-solution over >= 256 seeds must be statistically indistinguishable from
+    the reference's" — here for the kernel bench.py times (f32, BALANCED wide levels, warp-specialised persistent
+    kernel with a work queue cut into sub-chunks) on a formula large enough to use it: 256 replicas of a random 3-SAT
+    instance below the threshold, two-sample KS and Mann-Whitney against the f32 oracle's flag steps, and every flagged
+    replica's thresholded state verified exactly."""
+    from scipy import stats
+    monkeypatch.setenv("ODESAT_TILE_WS", "1")
+    monkeypatch.setenv("ODESAT_TILE_NT", "768")
+    monkeypatch.setenv("ODESAT_TILE_KSUB", "7")
+    f = cnf.random_ksat(4000, 3.0, seed=5)
+    D = S.DeviceFormula(f)
+    F = O.OracleFormula(f.varnum, f.clause_off, f.lits)
+    R, steps = 256, 600
+    v, xs, xl = F.init_batch(21, R, np.float32)
+    b = B.ReplicaBatch(D, R, L.F32, L.ENGINE_TILE, L.SCHED_BALANCED)
+    b.upload(v, xs, xl)
+    b.run_fixed(0.1, f.default_zeta(), steps, freeze=True)
+    st, _ = b.status()
+    gv, _, _ = b.download()
+    ver = b.verify()
+    b.close()
+    ost = F.batch_fixed(v, xs, xl, 0.1, f.default_zeta(), steps, freeze=True, nthreads=O.host_cores())
+    a = np.where(ost >= 0, ost, steps)
+    c = np.where(st >= 0, st, steps)
+    assert (ost >= 0).sum() > R // 2
+    assert stats.ks_2samp(a, c).pvalue > 0.01 and stats.mannwhitneyu(a, c).pvalue > 0.01
+    print(f"flag steps: oracle median {np.median(a)}, kernel median {np.median(c)}, identical for {(a == c).mean():.0%} of the replicas")
+    for r in np.flatnonzero(st >= 0)[:16]:
+        assert bool(ver[r]) == f.evaluate(gv[r] > 0)
+
+
+@pytest.mark.parametrize("prec", [L.F32, L.F64])
+@pytest.mark.parametrize("ksub", ["1", "3"])
+def test_exact_kernel_on_the_work_queue_is_bit_identical(monkeypatch, prec, ksub):
+    """The per-thread-ring kernel (EXACT schedule, the library default) as persistent CTAs taking (sub-chunk, tile) work
+    items: every sub-chunk of a tile may run on another SM; states, flag steps and frozen replicas equal the oracle's."""
+    monkeypatch.setenv("ODESAT_TILE_KSUB", ksub)
+    monkeypatch.setenv("ODESAT_TILE_QUEUE", "1")
+    f = cnf.random_ksat(4000, 3.0, seed=5)                        # flags between steps ~340 and ~450 at dt = 0.1
+    D = S.DeviceFormula(f)
+    F = O.OracleFormula(f.varnum, f.clause_off, f.lits)
+    dtype = B.np_dtype(prec)
+    R = 203
+    v, xs, xl = F.init_batch(11, R, dtype)
+    b = B.ReplicaBatch(D, R, prec, L.ENGINE_TILE, L.SCHED_EXACT)
+    b.upload(v, xs, xl)
+    for n in (1, 330, 69):
+        b.run_fixed(0.1, 0.001, n, freeze=True)
+    st, _ = b.status()
+    gv, gxs, gxl = b.download()
+    b.close()
+    ost = F.batch_fixed(v, xs, xl, 0.1, 0.001, 400, freeze=True, nthreads=O.host_cores())
+    assert 0 < (ost >= 0).sum() < R or (ost >= 0).all()
+    assert eq(st, ost) and eq(gv, v) and eq(gxs, xs) and eq(gxl, xl)
