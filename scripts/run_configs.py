@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """All five BASELINE.json configs on ONE B200 (multi-GPU configs: the per-GPU share).  Prints one JSON
-line per config; the committed copy is profiles/r01_configs.jsonl.  (bench.py is the contract benchmark
+line per config; the committed copy is profiles/rNN_configs.jsonl.  (bench.py is the contract benchmark
 and the only place the CPU oracle is timed — `bench.py --workload hard|rand10k|… ` prints `cpu_baseline`;
 this script runs product code only.)
 
@@ -73,7 +73,7 @@ def main():
         ms = run(steps, True)
         P = 4 if prec == L.F32 else 8
         by = algorithmic_bytes_per_step(f.varnum, f.n_clauses, f.n_literals, R, P, adaptive)
-        eng = {L.ENGINE_GATHER: "gather", L.ENGINE_TILE: "tile"}[b.engine]
+        eng = {L.ENGINE_GATHER: "gather", L.ENGINE_TILE: "tile", L.ENGINE_SLAB: "slab"}[b.engine]
         b.close()
         F.close()
         emit(config=cfg, what=what, engine=eng, precision="f32" if prec == L.F32 else "f64", ms_per_step=ms / steps,
