@@ -381,3 +381,28 @@ def test_exact_kernel_on_the_work_queue_is_bit_identical(monkeypatch, prec, ksub
     ost = F.batch_fixed(v, xs, xl, 0.1, 0.001, 400, freeze=True, nthreads=O.host_cores())
     assert 0 < (ost >= 0).sum() < R or (ost >= 0).all()
     assert eq(st, ost) and eq(gv, v) and eq(gxs, xs) and eq(gxl, xl)
+
+
+def test_warp_specialised_kernel_soak_4096_replicas_1024_steps(monkeypatch):
+    """Race evidence in lieu of compute-sanitizer (closed on this pool) for the kernel bench.py times: the full bench batch
+    — 4 096 replicas, N = 10 000, the benched width and ring (704 threads, four stages) — for 1 024 steps (16 launches;
+    producer warp, full / empty mbarriers, cross-proxy fences, work queue) must end BIT-IDENTICAL to the per-thread
+    cp.async ring walking the same schedule; and a 512-replica shard cut into sub-chunks of 5 steps (every tile hops
+    between SMs 13 times per launch) must equal the first 512 replicas of that run."""
+    f = cnf.random_ksat(10_000, 4.3, seed=20240611 + 2)
+    D = S.DeviceFormula(f)
+    monkeypatch.setenv("ODESAT_TILE_NT", "704")
+    monkeypatch.setenv("ODESAT_TILE_TMA", "0")
+    out = {}
+    for name, ws, R in (("ws", "1", 4096), ("ring", "0", 4096), ("shard", "1", 512)):
+        monkeypatch.setenv("ODESAT_TILE_WS", ws)
+        b = B.ReplicaBatch(D, R, L.F32, L.ENGINE_TILE, L.SCHED_BALANCED)
+        b.init(1, 0)
+        b.run_fixed(0.01, f.default_zeta(), 1024, freeze=False)
+        out[name] = b.download()
+        b.close()
+    for a, c in zip(out["ws"], out["ring"]):
+        assert eq(a, c)
+    for a, c in zip(out["shard"], out["ws"]):
+        assert eq(a, c[:512])
+    assert (np.abs(out["ws"][0]) == 1).mean() > 0.02
