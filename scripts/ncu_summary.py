@@ -78,7 +78,7 @@ def main():
                 rows = blocks[k][1:]
                 tot = sum(int(r[ix["# Samples"]]) for r in rows) or 1
                 print(f"top stalled SASS instructions (of {tot} samples):")
-                for r in sorted(rows, key=lambda r: -int(r[ix["# Samples"]]))[:10]:
+                for r in sorted(rows, key=lambda r: -int(r[ix["# Samples"]]))[:int(__import__("os").environ.get("NCU_TOP", "10"))]:
                     st2 = {h: int(r[ix[h]]) for h in h2 if h.startswith("stall_") and "(Not" not in h and int(r[ix[h]]) > 0}
                     top = ", ".join(f"{a.replace('stall_', '')} {b}" for a, b in sorted(st2.items(), key=lambda kv: -kv[1])[:2])
                     print(f"   {100.0 * int(r[ix['# Samples']]) / tot:5.1f}%  {r[ix['Source']].strip()[:64]:64s} {top}")
