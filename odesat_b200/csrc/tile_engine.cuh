@@ -1021,7 +1021,7 @@ template <typename T> struct TileEngine final : TileBase<T> {
             }
             return it->second;
         };
-        static const int cand[] = {128, 512, 640, 672, 704, 736, 768, 1024};
+        static const int cand[] = {128, 512, 640, 704, 768, 1024};
         if (const char* e = std::getenv("ODESAT_TILE_CHUNK")) { const int v = std::atoi(e); if (v > 0) chunk = v; }
         std::shared_ptr<TileLevels> lv;
         {   // small-instance mode: every level fits in a warp and the whole tile state fits in shared memory
@@ -1065,7 +1065,6 @@ template <typename T> struct TileEngine final : TileBase<T> {
                 // (N = 10 000: 160 KB + 4 x 16.5 KB), which the warp-specialised kernel turns into 2 % (measured
                 // in one run: 0.5302 ms/step against 0.5417 at 768 threads with a ring of three; ncu showed the
                 // consumers of the 768-thread kernel waiting 1.5 cycles per issued instruction for ring data)
-                if ((c == 672 || c == 736) && !forced) continue;                             // experiments: only on request
                 if (c == 704 && !forced && !(sizeof(T) == 4 && kind == ODESAT_SCHED_BALANCED && ws_env != 0 &&
                                               pick_depth(f.N, 704, (int)(f.M / 704 + 256)) == 4)) continue;
                 if (pick_depth(f.N, c, (int)(f.M / c + 256)) < 2 && c != 128) continue;   // its ring would not fit
@@ -1086,7 +1085,7 @@ template <typename T> struct TileEngine final : TileBase<T> {
         depth = pick_depth(f.N, nt, (int)(f.M / nt + 3 * (int64_t)lv->bucket.size() + 16));
         if (depth < 2) throw Error(ODESAT_EUNSUPPORTED, "variables do not fit in shared memory");
         if (want >= 2 && want <= depth) depth = want;
-        if (nt == 672 || nt == 704 || nt == 736) depth = depth >= 4 ? 4 : 2;   // the only rings these widths are instantiated with
+        if (nt == 704) depth = depth >= 4 ? 4 : 2;   // the only rings this width is instantiated with
         const int wide = (kind == ODESAT_SCHED_BALANCED && nt >= 512 && ipl != 1) ? 1 + ipl : 0;
         const int key = ((kind * 64 + nt / 32) * 16 + depth) + 65536 * wide;
         auto it = f.tile_sched.find(key);
@@ -1096,7 +1095,7 @@ template <typename T> struct TileEngine final : TileBase<T> {
         use_tma = tma_env >= 0 ? tma_env == 1 : (kind == ODESAT_SCHED_BALANCED && nt == 768 && depth % 3 == 0);
         // measured (B200, headline size, ms/step): f32 0.5315 against 0.5444 for the TMA kernel on the same wide levels and
         // 0.5554 for round 1's kernel and levels; f64 0.614 against 0.582 (TMA, wide) — so f64 keeps the TMA kernel
-        use_ws = ws_env >= 0 ? ws_env == 1 : (kind == ODESAT_SCHED_BALANCED && ((nt == 768 && depth % 3 == 0) || ((nt == 704 || nt == 672 || nt == 736) && depth == 4)) && sizeof(T) == 4);
+        use_ws = ws_env >= 0 ? ws_env == 1 : (kind == ODESAT_SCHED_BALANCED && ((nt == 768 && depth % 3 == 0) || (nt == 704 && depth == 4)) && sizeof(T) == 4);
         {   // the TMA kernel orders a slot's write-back against its next bulk read with a proxy fence issued at the start
             // of the next NON-EMPTY item: at least one such item must lie between the write and the wrap-around refill.
             // The warp-specialised kernel gates the re-read of a slot on the consumption of the stage's PREVIOUS item,
@@ -1272,7 +1271,8 @@ template <typename T> struct TileEngine final : TileBase<T> {
         ensure_max_smem(k_tile_small<T, STRICT>, (int)kMaxSmem, attr_devs);
         k_tile_small<T, STRICT><<<(unsigned)tiles, 32, smem_small(f.N, sched->n_items), stream>>>(a);
     }
-    // widths whose point is a ring of FOUR beside the rows of 10 000 variables: warp-specialised kernel, else the per-thread ring
+    // 704 threads: the width whose point is a ring of FOUR beside the rows of 10 000 variables (672 / 736 / 640 with the same
+    // ring and 576 with a ring of five were measured slower: DESIGN.md §5) — warp-specialised kernel, else the per-thread ring
     template <int NT> void launch_r4(const TileArgs<T>& a, bool strict) {
         if (strict) launch<NT, 2, true>(a);
         else if (!(use_ws && depth == 4 && launch_ws<NT, 4>(a))) {
@@ -1286,8 +1286,6 @@ template <typename T> struct TileEngine final : TileBase<T> {
         else if (nt == 640) launch_d<640>(a, strict);
         else if (nt == 768) launch_d<768>(a, strict);
         else if (nt == 704) launch_r4<704>(a, strict);
-        else if (nt == 672) launch_r4<672>(a, strict);
-        else if (nt == 736) launch_r4<736>(a, strict);
         else launch_d<1024>(a, strict);
     }
 
