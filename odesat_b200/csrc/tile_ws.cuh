@@ -43,7 +43,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 //                | full[D], empty[D] mbarriers | work word
 // Measured on B200 (headline size, f32, ms per step): releasing the stage at the END of the item 0.5395; releasing it
 // between the arithmetic and the stores (the asm statement pins ptxas' schedule there) 0.5596; clause words loaded
-// straight into registers one item ahead (ld.global.nc) instead of travelling through the ring 0.61 — both removed.
+// straight into registers one item ahead (ld.global.nc) instead of travelling through the ring 0.61 — both removed; the
+// producer also prefetching the cells of a later item into L2 (cp.async.bulk.prefetch.L2, 1–16 items beyond the ring)
+// 0.532–0.533 against 0.526 at 704 threads / ring of four — removed.
 template <typename T, int NT, int D>
 __global__ void __launch_bounds__(NT + 32, 1) k_tile_ws(const TileArgs<T> a, const TileWork wk) {
     constexpr int W = TileTraits<T>::W;
