@@ -25,6 +25,9 @@ struct BatchBase {
     int64_t launches = 0, dev_bytes = 0;
     int64_t step = 0;   // Euler steps issued since init/upload
     int device = 0;     // CUDA device that owns the buffers and the stream
+    // another shard's work on the SAME device is enqueued right behind this shard's (sub-batches of one call): its kernel
+    // fills this kernel's tail wave, so the tile engine need not cut the launch into sub-chunks to balance the SMs
+    bool followed = false;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // Early-exit words, KEY_SLOTS slots of {min key, unflagged replicas}: device copy (read by the next chunk's
@@ -500,6 +503,7 @@ template <typename T> struct BatchImpl final : BatchBase {
         if (tile) {
             if (canon_ahead) canon_to_tile();
             if (n > 0) canon_current = false;
+            tile->set_followed(followed);
             launches += tile->run_fixed((T)dt, (T)zeta, n, freeze, solved.p, step, stop_key);
             step += n;
             return;

@@ -323,6 +323,7 @@ void simulate_batch_impl(const odesat_formula* f, int64_t R, TH* v, TH* xs, TH* 
     sub = (int)std::max<int64_t>(1, std::min<int64_t>(sub, R / G));
     std::vector<Shard> sh = plan_shards(f, R, G, sub);
     cached_shards(f, sh, p->precision, eng, p->schedule);
+    for (size_t k = 0; k < sh.size(); ++k) sh[k].b->followed = k + 1 < sh.size() && sh[k + 1].dev == sh[k].dev;
     if (p->chunk <= 0) r.chunk = sh[0].b->preferred_chunk();
     const int64_t N = f->N, M = f->M;
     // main.rs:283-289: whatever the caller does not supply is generated on the device
