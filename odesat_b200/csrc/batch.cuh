@@ -18,6 +18,9 @@
 
 namespace odesat {
 
+// internal engine code (not part of the C ABI): AUTO restricted to engines that integrate adaptive steps
+constexpr int ENGINE_AUTO_ADAPTIVE = 16;
+
 struct BatchBase {
     const odesat_formula* f = nullptr;
     int64_t R = 0, Rp = 0;
@@ -127,6 +130,9 @@ template <typename T> struct BatchImpl final : BatchBase {
     std::unique_ptr<TileBase<T>> tile;   // TileEngine (one CTA per tile) or ClusterTileEngine (one cluster per replica)
 
     BatchImpl(const odesat_formula* f_, int64_t R_, int engine_, int schedule_) {
+        // AUTO for a run of adaptive steps: like AUTO, but only engines that have an adaptive kernel
+        const bool need_adaptive = engine_ == ENGINE_AUTO_ADAPTIVE;
+        if (need_adaptive) engine_ = ODESAT_ENGINE_AUTO;
         f = f_;
         R = R_;
         Rp = R >= 32 ? pad32(R) : R;
@@ -160,7 +166,7 @@ template <typename T> struct BatchImpl final : BatchBase {
         std::string why_s;
         const bool slab_ok = SlabEngine<T>::supports(*f, R, &why_s);
         if (engine_ == ODESAT_ENGINE_SLAB && !slab_ok) throw Error(ODESAT_EUNSUPPORTED, "slab engine cannot run this formula: " + why_s);
-        if (engine_ == ODESAT_ENGINE_SLAB || (engine_ == ODESAT_ENGINE_AUTO && engine == ODESAT_ENGINE_GATHER && slab_ok && SlabEngine<T>::preferred(*f, R)))
+        if (engine_ == ODESAT_ENGINE_SLAB || (engine_ == ODESAT_ENGINE_AUTO && !need_adaptive && engine == ODESAT_ENGINE_GATHER && slab_ok && SlabEngine<T>::preferred(*f, R)))
             engine = ODESAT_ENGINE_SLAB;
         const int64_t N = f->N, M = f->M;
         solved.alloc((size_t)std::max<int64_t>(Rp, 1), &dev_bytes);
@@ -180,6 +186,7 @@ template <typename T> struct BatchImpl final : BatchBase {
                 }
                 if (!tile) engine = ODESAT_ENGINE_GATHER;
             }
+            if (need_adaptive && tile && !tile->has_adaptive()) { tile.reset(); engine = ODESAT_ENGINE_GATHER; }
         }
         if (engine == ODESAT_ENGINE_SLAB) tile.reset(new SlabEngine<T>(*f, R, stream, &dev_bytes));
         if (!tile) {
@@ -546,7 +553,13 @@ template <typename T> struct BatchImpl final : BatchBase {
     void run_adaptive_async(double tol, double zeta, int64_t n) override {
         ODESAT_REQUIRE(n >= 0, "negative step count");
         ODESAT_REQUIRE(step + n < (int64_t(1) << 31) - 4, "step counter overflow");
-        if (tile) throw Error(ODESAT_EUNSUPPORTED, "the tile engine integrates fixed steps only; use the gather engine for adaptive steps");
+        if (tile) {   // tile_adaptive.cuh (throws ODESAT_EUNSUPPORTED on engines / formulas without an adaptive kernel)
+            if (canon_ahead) canon_to_tile();
+            if (n > 0) canon_current = false;
+            launches += tile->run_adaptive((T)tol, (T)zeta, n, solved.p, step, dtv.p);
+            step += n;
+            return;
+        }
         if (small_ok(true)) {
             run_small(true, 0.0, tol, zeta, n, 1, nullptr);
             step += n;

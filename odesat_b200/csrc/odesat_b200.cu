@@ -42,7 +42,7 @@ BatchBase* make_batch(const odesat_formula* f, int64_t R, int precision, int eng
     ODESAT_REQUIRE(f != nullptr, "formula is NULL");
     ODESAT_REQUIRE(R >= 0, "negative replica count");
     ODESAT_REQUIRE(precision == ODESAT_F64 || precision == ODESAT_F32, "unknown precision");
-    ODESAT_REQUIRE(engine >= ODESAT_ENGINE_AUTO && engine <= ODESAT_ENGINE_SLAB, "unknown engine");
+    ODESAT_REQUIRE((engine >= ODESAT_ENGINE_AUTO && engine <= ODESAT_ENGINE_SLAB) || engine == ENGINE_AUTO_ADAPTIVE, "unknown engine");
     ODESAT_REQUIRE(schedule == ODESAT_SCHED_EXACT || schedule == ODESAT_SCHED_BALANCED, "unknown schedule");
     require_device();
     int dev = 0;
@@ -309,9 +309,10 @@ void simulate_batch_impl(const odesat_formula* f, int64_t R, TH* v, TH* xs, TH* 
         if (assignment) std::memset(assignment, 0, (size_t)f->N);
         return;
     }
-    // the tile engine integrates fixed steps only: adaptive runs resolve AUTO to the gather engine
-    const int eng = (!r.fixed && p->engine == ODESAT_ENGINE_AUTO) ? ODESAT_ENGINE_GATHER : p->engine;
     const bool inter_adaptive = mode == ODESAT_MODE_INTER && !r.fixed;   // one dt shared by all replicas: sequential (Q7)
+    // adaptive runs: AUTO takes the tile engine only where it has an adaptive kernel (tile_adaptive.cuh); the
+    // sequential adaptive `inter` runs on the gather engine
+    const int eng = (!r.fixed && p->engine == ODESAT_ENGINE_AUTO) ? (inter_adaptive ? ODESAT_ENGINE_GATHER : ENGINE_AUTO_ADAPTIVE) : p->engine;
     if (inter_adaptive) G = 1;
     G = (int)std::min<int64_t>(G, R);
     int sub = p->sub_batches;

@@ -1,0 +1,326 @@
+// tile_adaptive.cuh — ADAPTIVE Euler steps (system.rs:111-139) in the tile engine (included by tile_engine.cuh).
+//
+// `batch` without -s and `solve` integrate with the step-doubling controller of euler_step: per step two RHS
+// evaluations (k1 on y, k2 on y_half), three updates, the ∞-norm of y_full − y_new and a new dt, per replica
+// (main.rs:278-308 runs `simulate` once per replica).  Round 1 ran this on the gather engine only: five launches per
+// step, y_half / y_full materialised in HBM, contributions written and re-read.  Here one CTA owns a replica tile for a
+// whole chunk of adaptive steps, exactly like k_tile_fixed: {v, dv} rows in shared memory, clauses streamed level by
+// level in the order of the compiled schedule (tile_schedule.hpp), one thread = one clause slot, the per-thread
+// cp.async ring.  A step is two walks over the schedule:
+//
+//   pass A   k1 = f(y):  reads {xs, xl} and gathers v, accumulates dv, raises the all-satisfied flag (the only RHS
+//            whose flag the reference uses, :120) and stores C_m — ONE scalar per clause and replica — instead of
+//            the half- and full-step memories: dxs and dxl are functions of (xs, xl, C_m) alone (:84-85), so pass B
+//            recomputes xs_half, xl_half, xs_full, xl_full bit for bit from the untouched {xs, xl} and C_m.
+//            Variable pass A: v_full → a global scratch row (read back by the same thread), rows ← {v_half, 0}.
+//            A replica whose flag is up is frozen here: "state untouched" (:122) costs nothing because pass A has
+//            not written any state yet.
+//   pass B   k2 = f(y_half): rebuilds the half/full memories, gathers v_half, accumulates dv, writes
+//            {xs_new, xl_new} in place and folds |y_full − y_new| of the memories into a per-thread maximum.
+//            Variable pass B: v_new = clamp(v_half + (dt/2)·dv), |v_full − v_new|; the error is reduced per replica
+//            (warp reduce + shared-memory integer max on the bit pattern: NaN-ignoring like the folds of max_error,
+//            :101-109) and every thread computes the replica's next dt (:133-135).
+//
+// HBM traffic per clause, replica and adaptive step: {xs, xl} read twice and written once + C_m written and read =
+// 8 scalars, against 12 for the materialising form of SURVEY §8(d) (read y, write y_half and y_full; read both, write
+// y_new); v never leaves the SM inside a chunk (v_full: 2 scalars per VARIABLE).
+//
+// Arithmetic: the statements of system.rs in their order (STRICT) or the tile kernel's fast forms that are bit-identical
+// on the domain the integrator lives in (clause_math in tile_engine.cuh) — so with the EXACT schedule every replica's
+// trajectory, dt sequence and flag step equal the oracle's bit for bit (tests/test_gpu_tile_adaptive.py).
+#pragma once
+
+namespace odesat {
+
+template <typename T> struct TileAdaptArgs {
+    TileArgs<T> t;          // geometry, schedule, state, flags, zeta, xl_max, step0 / nsteps, stop_key, oor (dt unused)
+    T* vfull = nullptr;     // [tiles][N][W]     v of the full step (scratch)
+    T* cm = nullptr;        // [tiles][Mpad][W]  C_m of pass A (scratch)
+    T* dt = nullptr;        // [R] per-replica step size, read at launch start, written back at its end
+    T tol = T(0);
+};
+
+// One RHS evaluation of a clause for one replica (system.rs:43-88) without the update: contributions added into d,
+// C_m returned.  Same two code paths as clause_math.
+template <typename T, bool STRICT>
+__device__ __forceinline__ T clause_rhs(const T (&v)[3], T (&d)[3], const T (&q)[3], T xs, T xl, T zeta) {
+    T a[3], mn, sm;
+    if (STRICT) {
+        mn = inf_v<T>();
+        sm = inf_v<T>();
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            a[j] = T(1) - q[j] * v[j];                                      // :49
+            if (a[j] < mn) { sm = mn; mn = a[j]; } else if (a[j] < sm) { sm = a[j]; }   // :50-55
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) a[j] = fma_exact(-q[j], v[j], T(1));
+        const T lo = rmin(a[0], a[1]), hi = rmax(a[0], a[1]);
+        mn = rmin(lo, a[2]);
+        sm = rmax(lo, rmin(hi, a[2]));
+    }
+    const T cm = T(0.5) * mn;                                               // :60
+    const T wgt = xl * xs;
+    if (STRICT) {
+        const T rg = (T(1) + zeta * xl) * (T(1) - xs);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const T g = (T(0.5) * q[j]) * ((a[j] != mn) ? mn : sm);         // :64-70
+            const T r = (cm == a[j]) ? T(0.5) * (q[j] - v[j]) : T(0);       // :73-77
+            d[j] = d[j] + (wgt * g + rg * r);                               // :80
+        }
+    } else {
+        const T h = T(0.5) * wgt;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) d[j] = fma_exact(h * ((a[j] != mn) ? mn : sm), q[j], d[j]);
+    }
+    return cm;
+}
+
+// a C_m cell: W scalars = 8 bytes
+__device__ __forceinline__ uint2 pack_cm(const float (&c)[2]) { return make_uint2(__float_as_uint(c[0]), __float_as_uint(c[1])); }
+__device__ __forceinline__ uint2 pack_cm(const double (&c)[1]) { return make_uint2((unsigned)__double2loint(c[0]), (unsigned)__double2hiint(c[0])); }
+__device__ __forceinline__ void unpack_cm(const uint2 u, float (&c)[2]) { c[0] = __uint_as_float(u.x); c[1] = __uint_as_float(u.y); }
+__device__ __forceinline__ void unpack_cm(const uint2 u, double (&c)[1]) { c[0] = __hiloint2double((int)u.y, (int)u.x); }
+
+template <typename U> __device__ __forceinline__ U warp_max_bits(U x);
+template <> __device__ __forceinline__ unsigned warp_max_bits<unsigned>(unsigned x) { return __reduce_max_sync(0xFFFFFFFFu, x); }
+template <> __device__ __forceinline__ unsigned long long warp_max_bits<unsigned long long>(unsigned long long x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long y = __shfl_xor_sync(0xFFFFFFFFu, x, o);
+        x = y > x ? y : x;
+    }
+    return x;
+}
+
+// Shared memory: rows[N] (16 B) | ring_m[D][NT] (16 B) | ring_e[D][NT] (8 B) | ring_c[D][NT] (8 B) | items[n_items]
+template <typename T, int NT, int D, bool STRICT>
+__global__ void __launch_bounds__(NT, 1) k_tile_adaptive(const TileAdaptArgs<T> aa) {
+    constexpr int W = TileTraits<T>::W;
+    using Row = typename TileTraits<T>::Row;
+    using Mem = typename TileTraits<T>::Mem;
+    using IO = RowIO<T, W>;
+    using EB = ErrBits<T>;
+    using U = typename EB::U;
+    static_assert(sizeof(T) * W == 8, "a C_m cell is 8 bytes");
+    const TileArgs<T>& a = aa.t;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Row* rows = reinterpret_cast<Row*>(smem_raw);
+    Mem* ring_m = reinterpret_cast<Mem*>(smem_raw + (size_t)a.N * sizeof(Row));
+    uint2* ring_e = reinterpret_cast<uint2*>(ring_m + D * NT);
+    uint2* ring_c = ring_e + D * NT;
+    uint2* s_items = ring_c + D * NT;   // {slot base, count | last << 31}
+    __shared__ U s_err[W];
+
+    const int s_first = launch_first_step<STRICT>(a);   // block-uniform
+    if (s_first >= a.nsteps) return;
+    const unsigned tid = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    const int n_items = a.n_items;
+    const uint2* my_entry = reinterpret_cast<const uint2*>(a.entry) + tid;      // + slot base
+    Mem* my_mem = a.mem + tile * a.Mpad + tid;                                  // + slot base
+    uint2* my_cm = reinterpret_cast<uint2*>(aa.cm) + tile * a.Mpad + tid;       // + slot base
+    Mem* my_cell_m = ring_m + tid;                                              // + k·NT
+    uint2* my_cell_e = ring_e + tid;
+    uint2* my_cell_c = ring_c + tid;
+    T* vt = a.vt + tile * a.N * W;
+    T* vfull = aa.vfull + tile * a.N * W;
+
+    for (int i = tid; i < n_items; i += NT) {
+        const uint32_t it = a.items[i];
+        s_items[i] = make_uint2(it & 0xFFFFFu, ((it >> 20) & 0x7FFu) | (it & TILE_ITEM_LAST));
+    }
+    for (int i = tid; i < a.N; i += NT) {
+        T v[W], dv[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) { v[w] = vt[(int64_t)i * W + w]; dv[w] = T(0); }
+        rows[i] = IO::pack(v, dv);
+    }
+    if (tid < W) s_err[tid] = EB::NONE;
+    bool valid[W], frozen[W];
+    int32_t solved_at[W];
+    T dtw[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        valid[w] = tile * W + w < a.R;
+        solved_at[w] = valid[w] ? a.solved[tile * W + w] : 0;
+        frozen[w] = !valid[w] || solved_at[w] >= 0;      // a flagged replica is never evaluated again (system.rs:229-231)
+        dtw[w] = valid[w] ? aa.dt[tile * W + w] : T(0.01);
+    }
+    __syncthreads();
+
+    // ring: item i of pass p sits in stage i % D; pass B's cells carry C_m as well
+    auto fetch = [&](int k, const uint2 it, bool with_cm) {
+        if (tid < (it.y & 0x7FFFFFFFu)) {
+            cp_async16(my_cell_m + k * NT, at16(my_mem, it.x));
+            cp_async8(my_cell_e + k * NT, at8(my_entry, it.x));
+            if (with_cm) cp_async8(my_cell_c + k * NT, at8(my_cm, it.x));
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int k = 0; k < D; ++k) fetch(k, s_items[k], false);
+
+    const T hi_s = T(1) - Kc<T>::EPSILON;
+    for (int s = s_first; s < a.nsteps; ++s) {
+        bool all_frozen = true;
+#pragma unroll
+        for (int w = 0; w < W; ++w) all_frozen = all_frozen && frozen[w];
+        if (all_frozen) break;
+        bool unsat[W];
+        U e_loc[W];
+        T hw[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) { unsat[w] = false; e_loc[w] = EB::NONE; hw[w] = T(0.5) * dtw[w]; }   // :128
+
+        for (int pass = 0; pass < 2; ++pass) {
+            // ------------------------------ clause phase ---------------------------------------
+            for (int base = 0; base < n_items; base += D) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    const int i = base + k;
+                    const uint2 it = s_items[i];
+                    cp_async_wait<D - 1>();                     // this thread's cells of item i have landed
+                    if (tid < (it.y & 0x7FFFFFFFu)) {
+                        const Mem mm = my_cell_m[k * NT];
+                        const uint2 e = my_cell_e[k * NT];
+                        Row* const r0 = reinterpret_cast<Row*>(smem_raw + (e.x & 0x3FFF0u));
+                        Row* const r1 = reinterpret_cast<Row*>(smem_raw + ((e.x >> 14) & 0x3FFF0u));
+                        Row* const r2 = reinterpret_cast<Row*>(smem_raw + (e.y & 0x3FFF0u));
+                        const T q[3] = {(e.y >> 24) & 1u ? T(-1) : T(1), (e.y >> 25) & 1u ? T(-1) : T(1), (e.y >> 26) & 1u ? T(-1) : T(1)};
+                        T v[3][W], d[3][W], xs[W], xl[W];
+                        IO::unpack(*r0, v[0], d[0]);
+                        IO::unpack(*r1, v[1], d[1]);
+                        IO::unpack(*r2, v[2], d[2]);
+                        IO::unpack_mem(mm, xs, xl);
+                        if (pass == 0) {
+                            T cm[W];
+#pragma unroll
+                            for (int w = 0; w < W; ++w) {
+                                const T vv[3] = {v[0][w], v[1][w], v[2][w]};
+                                T dd[3] = {d[0][w], d[1][w], d[2][w]};
+                                cm[w] = clause_rhs<T, STRICT>(vv, dd, q, xs[w], xl[w], a.zeta);
+                                d[0][w] = dd[0]; d[1][w] = dd[1]; d[2][w] = dd[2];
+                                unsat[w] = unsat[w] || !(cm[w] < Kc<T>::GAMMA);                      // :88
+                            }
+                            // plain store (not .cg): the cp.async.ca of pass B reads it back through this SM's L1
+                            *at8(my_cm, it.x) = pack_cm(cm);
+                        } else {
+                            T cm1[W];
+                            unpack_cm(my_cell_c[k * NT], cm1);
+#pragma unroll
+                            for (int w = 0; w < W; ++w) {
+                                const T dxs1 = (Kc<T>::BETA * (xs[w] + Kc<T>::EPSILON)) * (cm1[w] - Kc<T>::GAMMA);   // :84
+                                const T dxl1 = Kc<T>::ALPHA * (cm1[w] - Kc<T>::DELTA);                               // :85
+                                const T xs_f = euler_clamp(xs[w], dxs1, dtw[w], Kc<T>::EPSILON, hi_s);               // :125
+                                const T xl_f = euler_clamp(xl[w], dxl1, dtw[w], T(1), a.xl_max);
+                                const T xs_h = euler_clamp(xs[w], dxs1, hw[w], Kc<T>::EPSILON, hi_s);                // :128
+                                const T xl_h = euler_clamp(xl[w], dxl1, hw[w], T(1), a.xl_max);
+                                const T vv[3] = {v[0][w], v[1][w], v[2][w]};
+                                T dd[3] = {d[0][w], d[1][w], d[2][w]};
+                                const T cm2 = clause_rhs<T, STRICT>(vv, dd, q, xs_h, xl_h, a.zeta);                  // :129
+                                d[0][w] = dd[0]; d[1][w] = dd[1]; d[2][w] = dd[2];
+                                const T dxs2 = (Kc<T>::BETA * (xs_h + Kc<T>::EPSILON)) * (cm2 - Kc<T>::GAMMA);
+                                const T dxl2 = Kc<T>::ALPHA * (cm2 - Kc<T>::DELTA);
+                                const T xs_n = euler_clamp(xs_h, dxs2, hw[w], Kc<T>::EPSILON, hi_s);                 // :130
+                                const T xl_n = euler_clamp(xl_h, dxl2, hw[w], T(1), a.xl_max);
+                                if (!frozen[w]) {
+                                    const T e1 = fabs(xs_f - xs_n), e2 = fabs(xl_f - xl_n);                         // :104-107
+                                    if (e1 == e1) { const U b = EB::enc(e1); e_loc[w] = b > e_loc[w] ? b : e_loc[w]; }
+                                    if (e2 == e2) { const U b = EB::enc(e2); e_loc[w] = b > e_loc[w] ? b : e_loc[w]; }
+                                    xs[w] = xs_n;
+                                    xl[w] = xl_n;
+                                }
+                            }
+                            __stcg(at16(my_mem, it.x), IO::pack_mem(xs, xl));
+                        }
+                        IO::store_dv(r0, d[0]);
+                        IO::store_dv(r1, d[1]);
+                        IO::store_dv(r2, d[2]);
+                    }
+                    {   // refill stage k with item i + D, wrapping into the other pass (of the next step after pass B)
+                        int nx = i + D;
+                        bool nb = pass != 0;
+                        if (nx >= n_items) { nx -= n_items; nb = !nb; }
+                        fetch(k, s_items[nx], nb);
+                    }
+                    if ((int)it.y < 0) __syncthreads();         // last item of a level: block-uniform
+                }
+            }
+            if (pass == 0) {
+                // -------------------- flag (:120-122) + variable pass A ---------------------------
+                unsigned any_unsat = 0;
+#pragma unroll
+                for (int w = 0; w < W; ++w) any_unsat |= (__syncthreads_or((int)unsat[w]) ? 1u : 0u) << w;
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                    if (!frozen[w] && !((any_unsat >> w) & 1u)) {   // all satisfied: state untouched, the loop of `simulate` ends
+                        solved_at[w] = a.step0 + s;
+                        if (tid == 0) a.solved[tile * W + w] = solved_at[w];
+                        frozen[w] = true;
+                    }
+                }
+                for (int i = tid; i < a.N; i += NT) {
+                    T v[W], dv[W], vf[W];
+                    IO::unpack(rows[i], v, dv);
+#pragma unroll
+                    for (int w = 0; w < W; ++w) {
+                        vf[w] = frozen[w] ? v[w] : euler_clamp(v[w], dv[w], dtw[w], T(-1), T(1));   // :125
+                        v[w] = frozen[w] ? v[w] : euler_clamp(v[w], dv[w], hw[w], T(-1), T(1));     // :128
+                        dv[w] = T(0);
+                        __stcg(vfull + (int64_t)i * W + w, vf[w]);
+                    }
+                    rows[i] = IO::pack(v, dv);
+                }
+                __syncthreads();
+            } else {
+                // -------------------- variable pass B (:130) + error norm + dt (:132-135) ---------
+                for (int i = tid; i < a.N; i += NT) {
+                    T v[W], dv[W];
+                    IO::unpack(rows[i], v, dv);
+#pragma unroll
+                    for (int w = 0; w < W; ++w) {
+                        if (!frozen[w]) {
+                            const T vf = __ldcg(vfull + (int64_t)i * W + w);
+                            v[w] = euler_clamp(v[w], dv[w], hw[w], T(-1), T(1));
+                            const T e = fabs(vf - v[w]);                                            // :102-103
+                            if (e == e) { const U b = EB::enc(e); e_loc[w] = b > e_loc[w] ? b : e_loc[w]; }
+                        }
+                        dv[w] = T(0);
+                    }
+                    rows[i] = IO::pack(v, dv);
+                }
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                    const U m = warp_max_bits<U>(e_loc[w]);
+                    if ((tid & 31u) == 0u && m != EB::NONE) atomicMax(&s_err[w], m);
+                }
+                __syncthreads();
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                    if (!frozen[w]) {
+                        const T e = EB::dec(s_err[w]);
+                        dtw[w] = rmax(rmin(dtw[w] * sqrt(aa.tol / e), T(1e3)), T(0.0078125));       // :133-135
+                    }
+                }
+                __syncthreads();
+                if (tid < W) s_err[tid] = EB::NONE;     // next written in the NEXT step's variable pass B, many barriers away
+            }
+        }
+    }
+    cp_async_wait<0>();
+    for (int i = tid; i < a.N; i += NT) {
+        T v[W], dv[W];
+        IO::unpack(rows[i], v, dv);
+#pragma unroll
+        for (int w = 0; w < W; ++w) vt[(int64_t)i * W + w] = v[w];
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int w = 0; w < W; ++w) if (valid[w]) aa.dt[tile * W + w] = dtw[w];
+    }
+}
+
+}  // namespace odesat

@@ -627,6 +627,7 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed_tma(const TileArgs<T> a) {
 
 }  // namespace odesat
 #include "tile_ws.cuh"
+#include "tile_adaptive.cuh"
 namespace odesat {
 
 // ---- small-instance persistent kernel ---------------------------------------------
@@ -926,6 +927,12 @@ template <typename T> struct TileBase {
     // enqueues n fixed steps (no host synchronisation); stop_key: see TileArgs; → launches
     virtual int64_t run_fixed(T dt, T zeta, int64_t n, int freeze, int32_t* solved, int64_t step0,
                               const unsigned long long* stop_key = nullptr) = 0;
+    // adaptive steps (system.rs:111-139) with one dt per replica (dt_arr[R], device, in/out); every flagged replica is
+    // frozen (its state untouched, :122).  Engines without it: has_adaptive() == false.
+    virtual bool has_adaptive() const { return false; }
+    virtual int64_t run_adaptive(T /*tol*/, T /*zeta*/, int64_t /*n*/, int32_t* /*solved*/, int64_t /*step0*/, T* /*dt_arr*/) {
+        throw Error(ODESAT_EUNSUPPORTED, "this engine integrates fixed steps only; use the gather engine for adaptive steps");
+    }
     // device-to-device copy of the whole tile-layout state, and back (lock-step `inter`: a chunk that overshot the
     // winning step is replayed from the chunk's start)
     virtual void snapshot() = 0;
@@ -1294,6 +1301,75 @@ template <typename T> struct TileEngine final : TileBase<T> {
         else if (nt == 768) launch_d<768>(a, strict);
         else if (nt == 704) launch_r4<704>(a, strict);
         else launch_d<1024>(a, strict);
+    }
+
+    // ---- adaptive steps (tile_adaptive.cuh) ----------------------------------------------------------------
+    DevBuf<T> vfull, cmb;   // scratch of the adaptive kernel, allocated on first use
+    static size_t smem_adaptive(int64_t N, int n_items, int nt, int d) { return (size_t)N * 16 + (size_t)nt * d * 32 + (size_t)(n_items + 2) * 8; }
+    // ring depth of the adaptive kernel (32-byte stages): 3 when the schedule was padded for it and it fits, else 2
+    int adaptive_depth() const {
+        if (small) return 0;
+        if (depth % 3 == 0 && smem_adaptive(f.N, sched->n_items, nt, 3) <= kMaxSmem) return 3;
+        return smem_adaptive(f.N, sched->n_items, nt, 2) <= kMaxSmem ? 2 : 0;
+    }
+    bool has_adaptive() const override { return adaptive_depth() != 0; }
+    template <int NT, int D, bool STRICT> void launch_adaptive(const TileAdaptArgs<T>& a) {
+        static uint64_t attr_devs = 0;
+        ensure_max_smem(k_tile_adaptive<T, NT, D, STRICT>, (int)kMaxSmem, attr_devs);
+        k_tile_adaptive<T, NT, D, STRICT><<<(unsigned)tiles, NT, smem_adaptive(f.N, sched->n_items, NT, D), stream>>>(a);
+    }
+    template <int NT> void launch_adaptive_nt(const TileAdaptArgs<T>& a, bool strict, int d) {
+        if (strict) launch_adaptive<NT, 2, true>(a);
+        else if (d == 3) launch_adaptive<NT, 3, false>(a);
+        else launch_adaptive<NT, 2, false>(a);
+    }
+    void launch_adaptive_any(const TileAdaptArgs<T>& a, bool strict, int d) {
+        if (nt == 128) launch_adaptive_nt<128>(a, strict, d);
+        else if (nt == 512) launch_adaptive_nt<512>(a, strict, d);
+        else if (nt == 640) launch_adaptive_nt<640>(a, strict, d);
+        else if (nt == 704) launch_adaptive_nt<704>(a, strict, d);
+        else if (nt == 768) launch_adaptive_nt<768>(a, strict, d);
+        else launch_adaptive_nt<1024>(a, strict, d);
+    }
+    int64_t run_adaptive(T tol, T zeta, int64_t n, int32_t* solved, int64_t step0, T* dt_arr) override {
+        const int d = adaptive_depth();
+        if (d == 0) throw Error(ODESAT_EUNSUPPORTED, "adaptive steps: the tile kernel's ring does not fit beside this formula's rows (or one-warp tiles); use the gather engine");
+        if (!vfull.p) { vfull.alloc(vt.n, ledger_); cmb.alloc((size_t)(tiles * sched->Mpad * W), ledger_); }
+        int64_t launches = 0;
+        const bool zeta_ok = std::isfinite((double)zeta);
+        for (int64_t done = 0; done < n;) {
+            const int64_t k = std::min<int64_t>(chunk, n - done);
+            TileAdaptArgs<T> a;
+            a.t.N = f.N; a.t.Mpad = sched->Mpad; a.t.R = R; a.t.n_items = sched->n_items;
+            a.t.items = sched->d_items.p; a.t.entry = sched->d_entry.p;
+            a.t.vt = vt.p; a.t.mem = mem.p; a.t.solved = solved;
+            a.t.zeta = zeta; a.t.xl_max = T(1e4) * T(f.M);
+            a.t.step0 = (int32_t)(step0 + done); a.t.nsteps = (int32_t)k; a.t.freeze = 1;
+            a.vfull = vfull.p; a.cm = cmb.p; a.dt = dt_arr; a.tol = tol;
+            if (!zeta_ok || (need_rterm && !oor_valid)) {   // the literal statements (see run_fixed)
+                a.t.nsteps = 1;
+                launch_adaptive_any(a, true, 2);
+                done += 1;
+                if (zeta_ok) need_rterm = false;
+                ++launches;
+            } else if (need_rterm) {                         // first launch after an import: STRICT / fast pair keyed on *oor
+                TileAdaptArgs<T> s1 = a;
+                s1.t.nsteps = 1;
+                s1.t.oor = oor.p;
+                launch_adaptive_any(s1, true, 2);
+                a.t.oor = oor.p;
+                launch_adaptive_any(a, false, d);
+                done += k;
+                need_rterm = false;
+                launches += 2;
+            } else {
+                launch_adaptive_any(a, false, d);
+                done += k;
+                ++launches;
+            }
+        }
+        ODESAT_CUDA(cudaGetLastError());
+        return launches;
     }
 
     int64_t run_fixed(T dt, T zeta, int64_t n, int freeze, int32_t* solved, int64_t step0,

@@ -1,0 +1,156 @@
+"""Adaptive Euler steps (system.rs:111-139) in the TILE engine (csrc/tile_adaptive.cuh) against the oracle and against the
+GATHER engine: with the EXACT schedule every replica's state, dt sequence and flag step are bit-identical; flagged
+replicas stop untouched (system.rs:122); states outside the fast-arithmetic domain take the literal first step."""
+import numpy as np
+import pytest
+
+from odesat_b200 import _lib as L
+from odesat_b200 import batch as B
+from odesat_b200 import cnf
+from odesat_b200 import system as S
+from oracle import oracle as O
+
+from helpers import random_state
+
+pytestmark = pytest.mark.gpu
+
+
+def eq(a, b):
+    return np.array_equal(a, b, equal_nan=True)
+
+
+def both(f):
+    return S.DeviceFormula(f), O.OracleFormula(f.varnum, f.clause_off, f.lits)
+
+
+@pytest.mark.parametrize("prec", [L.F64, L.F32])
+@pytest.mark.parametrize("R", [1, 2, 33, 130])
+def test_tile_adaptive_exact_vs_oracle_ragged_replica_counts(prec, R, monkeypatch):
+    monkeypatch.setenv("ODESAT_TILE_SMALL", "0")             # the block-wide kernels, not the one-warp-per-tile kernel
+    f = cnf.random_ksat(500, 4.3, seed=12)
+    D, F = both(f)
+    dtype = B.np_dtype(prec)
+    b = B.ReplicaBatch(D, R, prec, L.ENGINE_TILE, L.SCHED_EXACT)
+    assert b.engine == L.ENGINE_TILE
+    v, xs, xl = F.init_batch(4, R, dtype)
+    b.upload(v, xs, xl)
+    for n in (1, 70, 59):                                     # 130 steps: crosses the 64-step launch chunk
+        b.run_adaptive(1e-3, 0.001, n)
+    ost, odt = F.batch_adaptive(v, xs, xl, 1e-3, 0.001, 130, nthreads=4)
+    gv, gxs, gxl = b.download()
+    gst, _ = b.status()
+    assert eq(gst, ost) and eq(b.dt(), odt)
+    assert eq(gv, v) and eq(gxs, xs) and eq(gxl, xl)
+    assert len(np.unique(odt)) > 1 or R == 1                  # the controller really moved the step sizes apart
+
+
+@pytest.mark.parametrize("prec", [L.F64, L.F32])
+def test_tile_adaptive_flagged_replicas_stop_untouched(prec, monkeypatch):
+    """An easy instance: the replicas flag at different steps (231 … 400); each must keep the state that satisfied the
+    check (system.rs:122) and its dt while its tile mate goes on."""
+    monkeypatch.setenv("ODESAT_TILE_SMALL", "0")
+    f = cnf.random_ksat(300, 2.0, seed=5)
+    D, F = both(f)
+    dtype = B.np_dtype(prec)
+    R = 41
+    b = B.ReplicaBatch(D, R, prec, L.ENGINE_TILE, L.SCHED_EXACT)
+    g = B.ReplicaBatch(D, R, prec, L.ENGINE_GATHER)
+    v, xs, xl = F.init_batch(9, R, dtype)
+    b.upload(v, xs, xl)
+    g.upload(v, xs, xl)
+    for n in (200, 100, 50):
+        b.run_adaptive(1e-3, f.default_zeta(), n)
+        g.run_adaptive(1e-3, f.default_zeta(), n)
+    ost, odt = F.batch_adaptive(v, xs, xl, 1e-3, f.default_zeta(), 350, nthreads=4)
+    assert 3 <= (ost >= 0).sum() < R                          # some flagged on the way, some still run
+    gst, _ = b.status()
+    gv, gxs, gxl = b.download()
+    assert eq(gst, ost) and eq(b.dt(), odt)
+    assert eq(gv, v) and eq(gxs, xs) and eq(gxl, xl)
+    hst, _ = g.status()
+    hv, hxs, hxl = g.download()
+    assert eq(hst, ost) and eq(hv, v) and eq(hxs, xs) and eq(hxl, xl) and eq(g.dt(), odt)
+    # exact verification of the flagged replicas' thresholded states (cnf.rs:246-264)
+    ver = b.verify()
+    assert all(ver[r] == 1 for r in range(R) if ost[r] >= 0)
+
+
+@pytest.mark.parametrize("prec", [L.F64, L.F32])
+def test_tile_adaptive_first_step_outside_the_fast_domain(prec, monkeypatch):
+    """|v| > 1, raw memories and a large zeta: the first step runs the reference's statements literally (the device
+    decides), the rest the fast forms — bit-identical to the oracle throughout."""
+    monkeypatch.setenv("ODESAT_TILE_SMALL", "0")
+    f = cnf.random_ksat(200, 4.3, seed=3)
+    D, F = both(f)
+    dtype = B.np_dtype(prec)
+    rng = np.random.default_rng(5)
+    R = 16
+    v, xs, xl = random_state(rng, F.N, F.M, dtype, R=R)
+    v[:, ::7] = (rng.uniform(-3, 3, size=v[:, ::7].shape)).astype(dtype)
+    v[:, 1] = 3.0; v[:, 2] = 2.0
+    b = B.ReplicaBatch(D, R, prec, L.ENGINE_TILE, L.SCHED_EXACT)
+    for zeta in (0.5, float("inf")):
+        b.upload(v, xs, xl)
+        b.run_adaptive(1e-3, zeta, 6)
+        ov, oxs, oxl = v.copy(), xs.copy(), xl.copy()
+        ost, odt = F.batch_adaptive(ov, oxs, oxl, 1e-3, zeta, 6)
+        gv, gxs, gxl = b.download()
+        assert eq(gv, ov) and eq(gxs, oxs) and eq(gxl, oxl) and eq(b.dt(), odt)
+
+
+@pytest.mark.parametrize("prec", [L.F64, L.F32])
+def test_tile_adaptive_mid_size_auto_engine_and_balanced(prec):
+    """N = 3 000 (block-wide kernels by default): AUTO takes the tile engine for an adaptive batch; EXACT is bit-identical
+    to the oracle; BALANCED (dv summed in colour order) agrees within rounding over a few steps."""
+    f = cnf.random_ksat(3000, 4.3, seed=21)
+    D, F = both(f)
+    dtype = B.np_dtype(prec)
+    R = 24
+    v, xs, xl = F.init_batch(2, R, dtype)
+    ov, oxs, oxl = v.copy(), xs.copy(), xl.copy()
+    ost, odt = F.batch_adaptive(ov, oxs, oxl, 1e-3, f.default_zeta(), 12, nthreads=4)
+    b = B.ReplicaBatch(D, R, prec, L.ENGINE_AUTO, L.SCHED_EXACT)
+    assert b.engine == L.ENGINE_TILE
+    b.upload(v, xs, xl)
+    b.run_adaptive(1e-3, f.default_zeta(), 12)
+    gv, gxs, gxl = b.download()
+    assert eq(gv, ov) and eq(gxs, oxs) and eq(gxl, oxl) and eq(b.dt(), odt)
+    c = B.ReplicaBatch(D, R, prec, L.ENGINE_TILE, L.SCHED_BALANCED)
+    c.upload(v, xs, xl)
+    c.run_adaptive(1e-3, f.default_zeta(), 12)
+    cv, cxs, cxl = c.download()
+    tol = 1e-9 if prec == L.F64 else 2e-4
+    assert np.max(np.abs(cv - ov)) <= tol and np.max(np.abs(cxs - oxs)) <= tol
+    assert np.max(np.abs(cxl / oxl - 1)) <= tol and np.max(np.abs(c.dt() / odt - 1)) <= (1e-6 if prec == L.F64 else 1e-2)
+
+
+def test_tile_adaptive_headline_size_equals_gather_engine():
+    """The formula of BASELINE configs[2] (N = 10 000, alpha = 4.3), 64 replicas, f32, 40 adaptive steps: the tile kernel
+    (EXACT) and the gather engine — different kernels, different layouts — end in identical states and step sizes."""
+    f = cnf.random_ksat(10_000, 4.3, seed=20240611 + 2)
+    D = S.DeviceFormula(f)
+    R = 64
+    t = B.ReplicaBatch(D, R, L.F32, L.ENGINE_TILE, L.SCHED_EXACT)
+    g = B.ReplicaBatch(D, R, L.F32, L.ENGINE_GATHER)
+    t.init(1, 0)
+    g.init(1, 0)
+    t.run_adaptive(1e-3, f.default_zeta(), 40)
+    g.run_adaptive(1e-3, f.default_zeta(), 40)
+    tv, txs, txl = t.download()
+    gv, gxs, gxl = g.download()
+    assert eq(tv, gv) and eq(txs, gxs) and eq(txl, gxl) and eq(t.dt(), g.dt())
+
+
+def test_simulate_batch_adaptive_takes_the_tile_engine_and_matches_the_oracle(monkeypatch):
+    """`batch` without -s through the one-call C ABI (main.rs:278-308): per-replica flags and verification equal the
+    oracle's, whichever engine AUTO picks (the tile engine for this size)."""
+    monkeypatch.setenv("ODESAT_TILE_SMALL", "0")
+    f = cnf.random_ksat(300, 2.0, seed=5)
+    D, F = both(f)
+    R, steps = 40, 380
+    v, xs, xl = F.init_batch(9, R, np.float64)
+    res = B.simulate_batch(D, R, v=v.copy(), steps=steps, precision=L.F64, mode=L.MODE_BATCH)
+    ost, _ = F.batch_adaptive(v, xs, xl, 1e-3, f.default_zeta(), steps, nthreads=4)
+    assert eq(res.solved_step, ost)
+    exp = np.array([f.evaluate(v[r] > 0) for r in range(R)], np.uint8)
+    assert eq(res.verified, exp)
