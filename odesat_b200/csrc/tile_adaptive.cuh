@@ -95,6 +95,43 @@ template <> __device__ __forceinline__ unsigned long long warp_max_bits<unsigned
     return x;
 }
 
+// ---- the two f32 replicas of a tile at once (packed f32x2, same operations in the same order as the scalar fast path) ----
+// RHS of one clause (system.rs:43-80): contributions added into d, → the clause minimum (C_m = 0.5·min exactly)
+__device__ __forceinline__ float2 clause_rhs_f32x2(const float2 (&v)[3], float2 (&d)[3], const float (&q)[3], float2 xs, float2 xl) {
+    float2 a[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) a[j] = fma2(bc2(-q[j]), v[j], bc2(1.0f));
+    float2 mn, sm;
+    {
+        const float lo = rmin(a[0].x, a[1].x), hi = rmax(a[0].x, a[1].x);
+        mn.x = rmin(lo, a[2].x);
+        sm.x = rmax(lo, rmin(hi, a[2].x));
+    }
+    {
+        const float lo = rmin(a[0].y, a[1].y), hi = rmax(a[0].y, a[1].y);
+        mn.y = rmin(lo, a[2].y);
+        sm.y = rmax(lo, rmin(hi, a[2].y));
+    }
+    const float2 h = mul2(bc2(0.5f), mul2(xl, xs));
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float2 sel = make_float2((a[j].x != mn.x) ? mn.x : sm.x, (a[j].y != mn.y) ? mn.y : sm.y);
+        d[j] = fma2(mul2(h, sel), bc2(q[j]), d[j]);                         // :64-70, :80
+    }
+    return mn;
+}
+// y + dt·dy clamped: the product packed, the addition scalar (ptxas contracts a packed mul + add into FFMA2 even with
+// -fmad=false, which would round once instead of twice — see packed_f32x2.cuh)
+__device__ __forceinline__ float2 euler_clamp_f32x2(float2 y, float2 dy, float2 dt, float lo, float hi) {
+    const float2 p = mul2(dt, dy);
+    return make_float2(rmin(rmax(__fadd_rn(y.x, p.x), lo), hi), rmin(rmax(__fadd_rn(y.y, p.y), lo), hi));
+}
+// memory derivatives (system.rs:84-85) from C_m
+__device__ __forceinline__ void mem_derivs_f32x2(float2 xs, float2 cm, float2& dxs, float2& dxl) {
+    dxs = mul2(mul2(bc2(Kc<float>::BETA), add2(xs, bc2(Kc<float>::EPSILON))), add2(cm, bc2(-Kc<float>::GAMMA)));
+    dxl = mul2(bc2(Kc<float>::ALPHA), add2(cm, bc2(-Kc<float>::DELTA)));
+}
+
 // Shared memory: rows[N] (16 B) | ring_m[D][NT] (16 B) | ring_e[D][NT] (8 B) | ring_c[D][NT] (8 B) | items[n_items]
 template <typename T, int NT, int D, bool STRICT>
 __global__ void __launch_bounds__(NT, 1) k_tile_adaptive(const TileAdaptArgs<T> aa) {
@@ -118,7 +155,8 @@ __global__ void __launch_bounds__(NT, 1) k_tile_adaptive(const TileAdaptArgs<T> 
     if (s_first >= a.nsteps) return;
     const unsigned tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
-    const int n_items = a.n_items;
+    static_assert(D == 2 || D == 3, "the item table is allocated with two spare entries");
+    const int n_items = (a.n_items + D - 1) / D * D;
     const uint2* my_entry = reinterpret_cast<const uint2*>(a.entry) + tid;      // + slot base
     Mem* my_mem = a.mem + tile * a.Mpad + tid;                                  // + slot base
     uint2* my_cm = reinterpret_cast<uint2*>(aa.cm) + tile * a.Mpad + tid;       // + slot base
@@ -128,8 +166,9 @@ __global__ void __launch_bounds__(NT, 1) k_tile_adaptive(const TileAdaptArgs<T> 
     T* vt = a.vt + tile * a.N * W;
     T* vfull = aa.vfull + tile * a.N * W;
 
+    // the item list is walked in whole rings: padded here with empty items to a multiple of D (≤ a.n_items + 2 entries)
     for (int i = tid; i < n_items; i += NT) {
-        const uint32_t it = a.items[i];
+        const uint32_t it = i < a.n_items ? a.items[i] : 0u;
         s_items[i] = make_uint2(it & 0xFFFFFu, ((it >> 20) & 0x7FFu) | (it & TILE_ITEM_LAST));
     }
     for (int i = tid; i < a.N; i += NT) {
@@ -170,6 +209,7 @@ __global__ void __launch_bounds__(NT, 1) k_tile_adaptive(const TileAdaptArgs<T> 
         for (int w = 0; w < W; ++w) all_frozen = all_frozen && frozen[w];
         if (all_frozen) break;
         bool unsat[W];
+        float mx[2] = {0.0f, 0.0f};   // f32x2 fast path: running max of pass A's clause minima (→ unsat)
         U e_loc[W];
         T hw[W];
 #pragma unroll
@@ -195,7 +235,48 @@ __global__ void __launch_bounds__(NT, 1) k_tile_adaptive(const TileAdaptArgs<T> 
                         IO::unpack(*r1, v[1], d[1]);
                         IO::unpack(*r2, v[2], d[2]);
                         IO::unpack_mem(mm, xs, xl);
-                        if (pass == 0) {
+                        if constexpr (!STRICT && W == 2 && sizeof(T) == 4) {
+                            const float2 v2[3] = {make_float2(v[0][0], v[0][1]), make_float2(v[1][0], v[1][1]), make_float2(v[2][0], v[2][1])};
+                            float2 d2[3] = {make_float2(d[0][0], d[0][1]), make_float2(d[1][0], d[1][1]), make_float2(d[2][0], d[2][1])};
+                            const float qf[3] = {(float)q[0], (float)q[1], (float)q[2]};
+                            const float2 xs2 = make_float2(xs[0], xs[1]), xl2 = make_float2(xl[0], xl[1]);
+                            if (pass == 0) {
+                                const float2 mn = clause_rhs_f32x2(v2, d2, qf, xs2, xl2);
+                                mx[0] = rmax(mx[0], mn.x);              // :88 as a running maximum of the clause minima (packed_f32x2.cuh)
+                                mx[1] = rmax(mx[1], mn.y);
+                                const float2 cm = mul2(bc2(0.5f), mn);                                                   // :60
+                                *at8(my_cm, it.x) = make_uint2(__float_as_uint(cm.x), __float_as_uint(cm.y));
+                            } else {
+                                const uint2 cu = my_cell_c[k * NT];
+                                const float2 cm1 = make_float2(__uint_as_float(cu.x), __uint_as_float(cu.y));
+                                const float2 dt2 = make_float2(dtw[0], dtw[1]), h2 = make_float2(hw[0], hw[1]);
+                                float2 dxs1, dxl1, dxs2, dxl2;
+                                mem_derivs_f32x2(xs2, cm1, dxs1, dxl1);                                                  // :84-85
+                                const float2 xs_f = euler_clamp_f32x2(xs2, dxs1, dt2, Kc<float>::EPSILON, (float)hi_s);  // :125
+                                const float2 xl_f = euler_clamp_f32x2(xl2, dxl1, dt2, 1.0f, (float)a.xl_max);
+                                const float2 xs_h = euler_clamp_f32x2(xs2, dxs1, h2, Kc<float>::EPSILON, (float)hi_s);   // :128
+                                const float2 xl_h = euler_clamp_f32x2(xl2, dxl1, h2, 1.0f, (float)a.xl_max);
+                                const float2 mn = clause_rhs_f32x2(v2, d2, qf, xs_h, xl_h);                              // :129
+                                mem_derivs_f32x2(xs_h, mul2(bc2(0.5f), mn), dxs2, dxl2);
+                                const float2 xs_n = euler_clamp_f32x2(xs_h, dxs2, h2, Kc<float>::EPSILON, (float)hi_s);  // :130
+                                const float2 xl_n = euler_clamp_f32x2(xl_h, dxl2, h2, 1.0f, (float)a.xl_max);
+                                const float es[2] = {fabsf(__fsub_rn(xs_f.x, xs_n.x)), fabsf(__fsub_rn(xs_f.y, xs_n.y))};   // :104-107
+                                const float el[2] = {fabsf(__fsub_rn(xl_f.x, xl_n.x)), fabsf(__fsub_rn(xl_f.y, xl_n.y))};
+                                const float ns[2] = {xs_n.x, xs_n.y}, nl[2] = {xl_n.x, xl_n.y};
+#pragma unroll
+                                for (int w = 0; w < W; ++w) {
+                                    if (!frozen[w]) {
+                                        if (es[w] == es[w]) { const U b = (U)EB::enc((T)es[w]); e_loc[w] = b > e_loc[w] ? b : e_loc[w]; }
+                                        if (el[w] == el[w]) { const U b = (U)EB::enc((T)el[w]); e_loc[w] = b > e_loc[w] ? b : e_loc[w]; }
+                                        xs[w] = (T)ns[w];
+                                        xl[w] = (T)nl[w];
+                                    }
+                                }
+                                __stcg(at16(my_mem, it.x), IO::pack_mem(xs, xl));
+                            }
+#pragma unroll
+                            for (int j = 0; j < 3; ++j) { d[j][0] = d2[j].x; d[j][1] = d2[j].y; }
+                        } else if (pass == 0) {
                             T cm[W];
 #pragma unroll
                             for (int w = 0; w < W; ++w) {
@@ -251,6 +332,7 @@ __global__ void __launch_bounds__(NT, 1) k_tile_adaptive(const TileAdaptArgs<T> 
             }
             if (pass == 0) {
                 // -------------------- flag (:120-122) + variable pass A ---------------------------
+                if constexpr (!STRICT && W == 2 && sizeof(T) == 4) { unsat[0] = !(mx[0] < 0.5f); unsat[1] = !(mx[1] < 0.5f); }
                 unsigned any_unsat = 0;
 #pragma unroll
                 for (int w = 0; w < W; ++w) any_unsat |= (__syncthreads_or((int)unsat[w]) ? 1u : 0u) << w;
@@ -270,27 +352,41 @@ __global__ void __launch_bounds__(NT, 1) k_tile_adaptive(const TileAdaptArgs<T> 
                         vf[w] = frozen[w] ? v[w] : euler_clamp(v[w], dv[w], dtw[w], T(-1), T(1));   // :125
                         v[w] = frozen[w] ? v[w] : euler_clamp(v[w], dv[w], hw[w], T(-1), T(1));     // :128
                         dv[w] = T(0);
-                        __stcg(vfull + (int64_t)i * W + w, vf[w]);
                     }
+                    __stcg(reinterpret_cast<uint2*>(vfull) + i, pack_cm(vf));
                     rows[i] = IO::pack(v, dv);
                 }
                 __syncthreads();
             } else {
                 // -------------------- variable pass B (:130) + error norm + dt (:132-135) ---------
-                for (int i = tid; i < a.N; i += NT) {
-                    T v[W], dv[W];
-                    IO::unpack(rows[i], v, dv);
+                // v_full comes back from L2: four rows' loads are issued before the first is used (ncu: a single dependent
+                // load per iteration left 7 % of the kernel's stall samples on the subtraction below)
+                for (int i0 = tid; i0 < a.N; i0 += 4 * NT) {
+                    uint2 vfu[4];
 #pragma unroll
-                    for (int w = 0; w < W; ++w) {
-                        if (!frozen[w]) {
-                            const T vf = __ldcg(vfull + (int64_t)i * W + w);
-                            v[w] = euler_clamp(v[w], dv[w], hw[w], T(-1), T(1));
-                            const T e = fabs(vf - v[w]);                                            // :102-103
-                            if (e == e) { const U b = EB::enc(e); e_loc[w] = b > e_loc[w] ? b : e_loc[w]; }
-                        }
-                        dv[w] = T(0);
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u * NT;
+                        vfu[u] = i < a.N ? __ldcg(reinterpret_cast<const uint2*>(vfull) + i) : make_uint2(0u, 0u);
                     }
-                    rows[i] = IO::pack(v, dv);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u * NT;
+                        if (i < a.N) {
+                            T v[W], dv[W], vf[W];
+                            IO::unpack(rows[i], v, dv);
+                            unpack_cm(vfu[u], vf);
+#pragma unroll
+                            for (int w = 0; w < W; ++w) {
+                                if (!frozen[w]) {
+                                    v[w] = euler_clamp(v[w], dv[w], hw[w], T(-1), T(1));
+                                    const T e = fabs(vf[w] - v[w]);                                 // :102-103
+                                    if (e == e) { const U b = EB::enc(e); e_loc[w] = b > e_loc[w] ? b : e_loc[w]; }
+                                }
+                                dv[w] = T(0);
+                            }
+                            rows[i] = IO::pack(v, dv);
+                        }
+                    }
                 }
 #pragma unroll
                 for (int w = 0; w < W; ++w) {

@@ -1307,9 +1307,11 @@ template <typename T> struct TileEngine final : TileBase<T> {
     DevBuf<T> vfull, cmb;   // scratch of the adaptive kernel, allocated on first use
     static size_t smem_adaptive(int64_t N, int n_items, int nt, int d) { return (size_t)N * 16 + (size_t)nt * d * 32 + (size_t)(n_items + 2) * 8; }
     // ring depth of the adaptive kernel (32-byte stages): 3 when the schedule was padded for it and it fits, else 2
+    // (the kernel pads the item list to whole rings itself, so any schedule will do; ODESAT_TILE_AD=2/3 overrides)
     int adaptive_depth() const {
         if (small) return 0;
-        if (depth % 3 == 0 && smem_adaptive(f.N, sched->n_items, nt, 3) <= kMaxSmem) return 3;
+        static const int env = [] { const char* e = std::getenv("ODESAT_TILE_AD"); return e ? std::atoi(e) : 0; }();
+        if (env != 2 && smem_adaptive(f.N, sched->n_items, nt, 3) <= kMaxSmem) return 3;
         return smem_adaptive(f.N, sched->n_items, nt, 2) <= kMaxSmem ? 2 : 0;
     }
     bool has_adaptive() const override { return adaptive_depth() != 0; }
