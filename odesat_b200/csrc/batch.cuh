@@ -152,7 +152,12 @@ template <typename T> struct BatchImpl final : BatchBase {
         const bool force_c = ClusterTileEngine<T>::forced_cluster() != 0;
         if (engine_ == ODESAT_ENGINE_TILE && !tile_ok && !ctile_ok)
             throw Error(ODESAT_EUNSUPPORTED, "tile engine cannot run this formula: " + why + "; " + why_c);
-        const bool want_tile = engine_ == ODESAT_ENGINE_TILE || (engine_ == ODESAT_ENGINE_AUTO && TileEngine<T>::preferred(*f, R));
+        // Measured on B200 (N = 10 000, 43 000 clauses of which 3 000 have 5 or 8 literals, 4 096 replicas, f32): loop clauses
+        // (tile_ragged.cuh) make the EXACT schedule's 94 one-item levels wait for one slow warp each — 2.54 ms/step against
+        // 1.66 on the gather engine — while BALANCED's wide levels absorb them (1.27).  One- and two-literal clauses cost
+        // nothing extra (0.66 / 0.62 ms against 1.60).
+        const bool loopy_exact = f->n_loopy > 0 && schedule_ == ODESAT_SCHED_EXACT;
+        const bool want_tile = engine_ == ODESAT_ENGINE_TILE || (engine_ == ODESAT_ENGINE_AUTO && TileEngine<T>::preferred(*f, R) && !loopy_exact);
         // Measured on B200 (N = 50 000, 2 048 replicas, f32): with 2 CTAs per replica the scattered 8-byte
         // distributed-shared-memory gathers go through the generic LD/ST path at one lane per cycle and the
         // step takes 12.3 ms against 7.3 ms for the general engine — so AUTO takes the cluster engine only

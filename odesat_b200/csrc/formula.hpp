@@ -25,6 +25,7 @@ struct odesat_formula {
     int K = 0;                       // uniform clause length (0 = ragged or M == 0)
     bool distinct_vars = true;       // no variable repeated inside a clause
     int max_degree = 0;              // max occurrences of a variable
+    int64_t n_loopy = 0;             // clauses with no literal, more than three, or a repeated variable (tile engine: loop clauses)
     int device = 0;
     std::vector<int64_t> h_off;      // [M+1]
     std::vector<int32_t> h_lits;     // [L]
@@ -109,8 +110,11 @@ struct odesat_formula {
         std::vector<int32_t> cur(h_voff.begin(), h_voff.end() - 1);
         h_xs0.resize(M);
         distinct_vars = true;
+        n_loopy = 0;
         for (int64_t m = 0; m < M; ++m) {
             bool anyneg = false;
+            const bool was_distinct = distinct_vars;
+            distinct_vars = true;
             for (int64_t j = h_off[m]; j < h_off[m + 1]; ++j) {
                 const int32_t l = h_lits[j];
                 const int32_t var = (l < 0 ? -l : l) - 1;
@@ -121,6 +125,9 @@ struct odesat_formula {
                 h_occ_slot[e] = (int32_t)j;
             }
             h_xs0[m] = anyneg ? 1 : -1;   // system.rs:362-372
+            const int64_t len = h_off[m + 1] - h_off[m];
+            if (len == 0 || len > 3 || !distinct_vars) ++n_loopy;
+            distinct_vars = distinct_vars && was_distinct;
         }
     }
 

@@ -620,7 +620,7 @@ int odesat_tile_schedule_stats(int64_t varnum, int64_t n_clauses, const int64_t*
         ODESAT_REQUIRE(threads >= 32 && threads <= 1024 && threads % 32 == 0 && depth >= 1 && depth <= 16, "bad threads/depth");
         odesat_formula f;
         f.build(varnum, n_clauses, clause_off, lits);
-        ODESAT_REQUIRE(f.K == 3 && f.distinct_vars, "tile schedules need uniform 3-literal clauses with distinct variables");
+        ODESAT_REQUIRE(f.M >= 1, "tile schedules need at least one clause");   // ragged lengths: loop clauses (tile_ragged.cuh)
         // the same level construction the tile engine uses for a CTA of `threads` threads
         auto lv = schedule == ODESAT_SCHED_EXACT ? build_tile_levels(f, schedule, threads) : build_balanced_levels(f, threads, tile_items_per_level());
         auto s = build_tile_schedule(f, *lv, schedule, threads, depth, /*upload=*/false);

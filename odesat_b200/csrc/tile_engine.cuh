@@ -628,6 +628,7 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed_tma(const TileArgs<T> a) {
 }  // namespace odesat
 #include "tile_ws.cuh"
 #include "tile_adaptive.cuh"
+#include "tile_ragged.cuh"
 namespace odesat {
 
 // ---- small-instance persistent kernel ---------------------------------------------
@@ -984,6 +985,7 @@ template <typename T> struct TileEngine final : TileBase<T> {
     int num_sms = 148;
     DevBuf<int> work;     // [1 + tiles] work-queue counter and per-tile published sub-chunks (k_tile_ws)
     bool small = false;   // one warp per tile, state resident in shared memory (k_tile_small)
+    bool ragged = false;  // some clause is not three distinct variables: k_tile_ragged (tile_ragged.cuh), fixed steps only
     int nt = 512;
     int chunk = 64;   // Euler steps per launch
     int depth = 6;    // prefetch ring depth (tunable for NT = 512 only)
@@ -1003,8 +1005,9 @@ template <typename T> struct TileEngine final : TileBase<T> {
     static bool supports(const odesat_formula& f, int64_t R, std::string* why) {
         auto no = [&](const char* m) { if (why) *why = m; return false; };
         if (R < 1) return no("empty batch");
-        if (f.K != 3) return no("needs uniform clause length 3");
-        if (!f.distinct_vars) return no("a clause repeats a variable");
+        // uniform 3-literal clauses with distinct variables: the packed kernels; anything else (ragged lengths, unit and
+        // empty clauses, a variable repeated inside a clause): k_tile_ragged, fixed steps
+        if (f.M < 1) return no("no clauses");
         if (f.N > 16383) return no("more than 16383 variables");
         // a 512-thread CTA with a ring of 2 and an item table sized for this formula must fit beside the rows
         // (a narrower CTA would fit a few more variables but cannot hide the shared-memory latency: the
@@ -1016,6 +1019,8 @@ template <typename T> struct TileEngine final : TileBase<T> {
 
     TileEngine(const odesat_formula& f_, int64_t R_, int kind, cudaStream_t st, int64_t* ledger) : f(f_), R(R_), stream(st), ledger_(ledger) {
         tiles = (R + W - 1) / W;
+        ragged = f.K != 3 || !f.distinct_vars;
+        if (ragged) { tma_env = 0; ws_env = 0; queue_fixed = false; }
         // levels: BALANCED colour classes do not depend on the CTA width; EXACT levels are list-scheduled
         // with the CTA width as the cap (one item per level), so they are built per candidate width
         auto levels_for = [&](int cap) {
@@ -1035,7 +1040,7 @@ template <typename T> struct TileEngine final : TileBase<T> {
         std::shared_ptr<TileLevels> lv;
         {   // small-instance mode: every level fits in a warp and the whole tile state fits in shared memory
             const char* e = std::getenv("ODESAT_TILE_SMALL");
-            if (f.M <= 8192 && !(e && e[0] == '0')) {
+            if (f.M <= 8192 && !ragged && !(e && e[0] == '0')) {
                 auto l32 = levels_for(32);
                 size_t maxlev = 0, items32 = 0;
                 for (const auto& b : l32->bucket) { maxlev = std::max(maxlev, b.size()); items32 += b.empty() ? 0 : 1; }
@@ -1070,6 +1075,7 @@ template <typename T> struct TileEngine final : TileBase<T> {
             double best = 1e300;
             for (int c : cand) {
                 if (forced && c != forced) continue;
+                if (ragged && c != 128 && c != 512) continue;   // widths k_tile_ragged is instantiated with
                 // 704 threads exist for one case: f32 BALANCED where a ring of FOUR stages then fits beside the rows
                 // (N = 10 000: 160 KB + 4 x 16.5 KB), which the warp-specialised kernel turns into 2 % (measured
                 // in one run: 0.5302 ms/step against 0.5417 at 768 threads with a ring of three; ncu showed the
@@ -1095,6 +1101,7 @@ template <typename T> struct TileEngine final : TileBase<T> {
         if (depth < 2) throw Error(ODESAT_EUNSUPPORTED, "variables do not fit in shared memory");
         if (want >= 2 && want <= depth) depth = want;
         if (nt == 704) depth = depth >= 4 ? 4 : 2;   // the only rings this width is instantiated with
+        if (ragged) depth = depth >= 6 ? 6 : (depth >= 4 ? 4 : 2);   // rings k_tile_ragged is instantiated with
         const int wide = (kind == ODESAT_SCHED_BALANCED && nt >= 512 && ipl != 1) ? 1 + ipl : 0;
         const int key = ((kind * 64 + nt / 32) * 16 + depth) + 65536 * wide;
         auto it = f.tile_sched.find(key);
@@ -1178,7 +1185,7 @@ template <typename T> struct TileEngine final : TileBase<T> {
         return 1;
     }
     int64_t verify_direct(uint32_t* bad) override {
-        if ((size_t)f.N > 48 * 1024) return 0;
+        if ((size_t)f.N > 48 * 1024 || ragged) return 0;   // k_tile_verify reads packed 3-literal entries
         k_tile_verify<T><<<(unsigned)tiles, 512, (size_t)f.N, stream>>>(vt.p, sched->d_entry.p, sched->d_perm.p, f.N, sched->Mpad, R, bad);
         ODESAT_CUDA(cudaGetLastError());
         return 1;
@@ -1293,7 +1300,19 @@ template <typename T> struct TileEngine final : TileBase<T> {
             if (depth >= 4) launch<NT, 4, false>(a); else launch<NT, 2, false>(a);
         }
     }
+    template <int NT, int D, bool STRICT> void launch_ragged(const TileArgs<T>& a) {
+        static uint64_t attr_devs = 0;
+        ensure_max_smem(k_tile_ragged<T, NT, D, STRICT>, (int)kMaxSmem, attr_devs);
+        k_tile_ragged<T, NT, D, STRICT><<<(unsigned)tiles, NT, smem_bytes(f.N, sched->n_items, NT, D), stream>>>(a, sched->d_aux.p);
+    }
+    template <int NT> void launch_ragged_nt(const TileArgs<T>& a, bool strict) {
+        if (strict) launch_ragged<NT, 2, true>(a);
+        else if (depth == 6) launch_ragged<NT, 6, false>(a);
+        else if (depth == 4) launch_ragged<NT, 4, false>(a);
+        else launch_ragged<NT, 2, false>(a);
+    }
     void launch_nt(const TileArgs<T>& a, bool strict) {
+        if (ragged) { if (nt == 128) launch_ragged_nt<128>(a, strict); else launch_ragged_nt<512>(a, strict); return; }
         if (small) { if (strict) launch_small<true>(a); else launch_small<false>(a); return; }
         if (nt == 128) launch_d<128>(a, strict);
         else if (nt == 512) launch_d<512>(a, strict);
@@ -1309,7 +1328,7 @@ template <typename T> struct TileEngine final : TileBase<T> {
     // ring depth of the adaptive kernel (32-byte stages): 3 when the schedule was padded for it and it fits, else 2
     // (the kernel pads the item list to whole rings itself, so any schedule will do; ODESAT_TILE_AD=2/3 overrides)
     int adaptive_depth() const {
-        if (small) return 0;
+        if (small || ragged) return 0;
         static const int env = [] { const char* e = std::getenv("ODESAT_TILE_AD"); return e ? std::atoi(e) : 0; }();
         if (env != 2 && smem_adaptive(f.N, sched->n_items, nt, 3) <= kMaxSmem) return 3;
         return smem_adaptive(f.N, sched->n_items, nt, 2) <= kMaxSmem ? 2 : 0;

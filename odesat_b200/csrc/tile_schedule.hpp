@@ -47,13 +47,30 @@ struct TileSchedule {
     std::vector<uint32_t> items;       // [n_items] packed (base, nvalid, last) — valid when nt <= 1024 and Mpad < 2^20
     std::vector<uint2> items2;         // [n_items] {base, nvalid | last << 31} — any width (cluster tiles)
     std::vector<int32_t> perm;         // [Mpad] slot → clause index, −1 = padding
-    std::vector<uint64_t> entry;       // [Mpad] packed clause: 3×16-bit row + sign bits + valid
+    std::vector<uint64_t> entry;       // [Mpad] packed clause: 3×16-bit row + sign bits + valid; or a LOOP clause (below)
+    std::vector<uint32_t> aux;         // literal words of the loop clauses: row byte offset | negated << 31, 4-word aligned per clause
+    int64_t n_loop = 0;                // loop clauses: no literal, more than three, or a repeated variable (tile_ragged.cuh)
     double conflict_wavefronts = 0;    // avg shared-memory wavefronts per quarter-warp access (1 = ideal)
     DevBuf<int32_t> d_perm;
     DevBuf<uint32_t> d_items;
     DevBuf<uint2> d_items2;
     DevBuf<uint64_t> d_entry;
+    DevBuf<uint32_t> d_aux;
 };
+
+// A clause with no literal, more than three, or a repeated variable (ragged formulas — `solve -r` output,
+// cnf.rs:397-416; SURVEY quirk Q9's empty clause) is a LOOP clause: its slot's entry holds {offset into TileSchedule::aux, length | TILE_ENTRY_LOOP} and the
+// kernel walks its literals (tile_ragged.cuh).  Bit 27 of the high word is clear in every 3-literal entry.
+constexpr uint32_t TILE_ENTRY_LOOP = 1u << 27;
+// Clauses of one or two literals (distinct variables) keep the packed word: the literal positions that do not exist are
+// flagged (TILE_ENTRY_NO2: no third literal, TILE_ENTRY_NO1: no second one either), their row offset is 0 and the kernel
+// gives them the value +inf, which is what min / second-min start from (system.rs:46-47).
+constexpr uint32_t TILE_ENTRY_NO2 = 1u << 28, TILE_ENTRY_NO1 = 1u << 29;
+// TILE_ENTRY_LOOP8: at most eight literals, all variables distinct — the kernel then takes all rows into registers at once
+constexpr uint32_t TILE_ENTRY_LOOP8 = 1u << 26;
+inline uint64_t pack_entry_loop(uint32_t aux_off, uint32_t len, bool distinct) {
+    return (uint64_t)aux_off | ((uint64_t)(len | TILE_ENTRY_LOOP | (distinct && len <= 8 ? TILE_ENTRY_LOOP8 : 0u)) << 32);
+}
 
 constexpr uint64_t TILE_VALID_BIT = 1ull << 51;
 
@@ -90,25 +107,33 @@ inline void pack_level(const odesat_formula& f, const std::vector<int32_t>& clau
     // Compact: no holes inside a level (measured on B200: spare hole slots improve the packing
     // from 1.23 to 1.12 wavefronts per access but cost more in extra warps and traffic).
     const size_t nb = (n + 7) / 8;
-    struct Cl { int32_t m; int32_t var[3]; bool neg[3]; };
+    struct Cl { int32_t m; int32_t var[3]; bool neg[3]; int len; };   // len < 3: positions len.. do not exist (var = -1)
     struct Bin { uint8_t mask[3] = {0, 0, 0}; uint8_t cnt[3][8] = {}; int filled = 0; Cl slot[8]; int cap = 8; };
     std::vector<Bin> bins(nb);
     if (n % 8) bins[nb - 1].cap = (int)(n % 8);   // the level's last octet is partial
     auto load = [&](int32_t m) {
         Cl c;
         c.m = m;
+        c.len = (int)std::min<int64_t>(3, f.h_off[m + 1] - f.h_off[m]);
         for (int j = 0; j < 3; ++j) {
+            if (j >= c.len) { c.var[j] = -1; c.neg[j] = false; continue; }
             const int32_t l = f.h_lits[f.h_off[m] + j];
             c.var[j] = (l < 0 ? -l : l) - 1;
             c.neg[j] = l < 0;
         }
         return c;
     };
+    // a permutation may only move literals that exist (the missing positions stay at the end)
+    auto allowed = [&](const Cl& c, int p) {
+        for (int j = c.len; j < 3; ++j) if (P[p][j] != j) return false;
+        return true;
+    };
     auto place = [&](Bin& b, const Cl& c, int p) {
         Cl q;
         q.m = c.m;
+        q.len = c.len;
         for (int j = 0; j < 3; ++j) { q.var[j] = c.var[P[p][j]]; q.neg[j] = c.neg[P[p][j]]; }
-        for (int j = 0; j < 3; ++j) { b.mask[j] |= (uint8_t)(1u << (q.var[j] & 7)); b.cnt[j][q.var[j] & 7]++; }
+        for (int j = 0; j < q.len; ++j) { b.mask[j] |= (uint8_t)(1u << (q.var[j] & 7)); b.cnt[j][q.var[j] & 7]++; }
         b.slot[b.filled++] = q;
     };
     std::vector<Cl> leftover;
@@ -121,8 +146,10 @@ inline void pack_level(const odesat_formula& f, const std::vector<int32_t>& clau
             Bin& b = bins[bi];
             if (b.filled >= b.cap) continue;
             for (int p = 0; p < 6 && !done; ++p) {
-                const int b0 = c.var[P[p][0]] & 7, b1 = c.var[P[p][1]] & 7, b2 = c.var[P[p][2]] & 7;
-                if (!((b.mask[0] >> b0) & 1) && !((b.mask[1] >> b1) & 1) && !((b.mask[2] >> b2) & 1)) {
+                if (!allowed(c, p)) continue;
+                bool free = true;
+                for (int j = 0; j < c.len; ++j) free = free && !((b.mask[j] >> (c.var[P[p][j]] & 7)) & 1);
+                if (free) {
                     place(b, c, p);
                     done = true;
                 }
@@ -137,8 +164,9 @@ inline void pack_level(const odesat_formula& f, const std::vector<int32_t>& clau
             Bin& b = bins[bi];
             if (b.filled >= b.cap) continue;
             for (int p = 0; p < 6; ++p) {
+                if (!allowed(c, p)) continue;
                 int cost = 0;
-                for (int j = 0; j < 3; ++j) {
+                for (int j = 0; j < c.len; ++j) {
                     const int r = c.var[P[p][j]] & 7;
                     int mx = 0;
                     for (int k = 0; k < 8; ++k) mx = std::max<int>(mx, b.cnt[j][k]);
@@ -156,7 +184,13 @@ inline void pack_level(const odesat_formula& f, const std::vector<int32_t>& clau
         for (int k = 0; k < 8; ++k) {
             if (k < b.filled) {
                 out_perm.push_back(b.slot[k].m);
-                out_entry.push_back(pack_entry3(b.slot[k].var, b.slot[k].neg, wide));
+                const Cl& c = b.slot[k];
+                if (c.len == 3) out_entry.push_back(pack_entry3(c.var, c.neg, wide));
+                else {   // one or two literals (never for the cluster kernel: ragged formulas are not `wide`)
+                    int32_t var[3] = {c.var[0], c.len > 1 ? c.var[1] : 0, 0};
+                    out_entry.push_back(pack_entry3(var, c.neg, false) |
+                                        ((uint64_t)(TILE_ENTRY_NO2 | (c.len < 2 ? TILE_ENTRY_NO1 : 0u)) << 32));
+                }
             } else if (bi != last_used) {   // cannot happen with compact bins; kept as a guard
                 out_perm.push_back(-1);
                 out_entry.push_back(0);
@@ -192,6 +226,7 @@ inline std::shared_ptr<TileLevels> build_tile_levels(const odesat_formula& f, in
         const int32_t l = f.h_lits[f.h_off[m] + j];
         return (l < 0 ? -l : l) - 1;
     };
+    auto len_of = [&](int64_t m) { return (int)(f.h_off[m + 1] - f.h_off[m]); };   // 3 everywhere for the uniform formulas
     if (kind == ODESAT_SCHED_EXACT) {
         // Order-preserving levels by LIST SCHEDULING: clause m may run once the previous clause of each of
         // its variables has run in an EARLIER level (so every variable still meets its clauses in ascending
@@ -200,16 +235,18 @@ inline std::shared_ptr<TileLevels> build_tile_levels(const odesat_formula& f, in
         // dependency chain hanging off the clause).  On random 3-SAT the level count stays at the critical
         // path (94 at N = 10 000) while the item count drops from 121 to 94 for 512-thread CTAs.
         // target <= 0: as soon as possible, no cap.
-        std::vector<int32_t> succ((size_t)M * 3, -1), npred(M, 0), last_slot(N, -1), height(M, 0);
+        // succ is indexed by literal slot (h_off[m] + j: 3m + j for uniform 3-literal clauses)
+        std::vector<int32_t> succ((size_t)f.L, -1), npred(M, 0), last_slot(N, -1), height(M, 0);
         for (int64_t m = 0; m < M; ++m)
-            for (int j = 0; j < 3; ++j) {
+            for (int j = 0; j < len_of(m); ++j) {
                 const int32_t v = var_of(m, j);
-                if (last_slot[v] >= 0) { succ[last_slot[v]] = (int32_t)m; ++npred[m]; }
-                last_slot[v] = (int32_t)(m * 3 + j);
+                // (a variable repeated inside a clause is no dependency: a loop clause adds its literals in order)
+                if (last_slot[v] >= 0 && last_slot[v] < f.h_off[m]) { succ[last_slot[v]] = (int32_t)m; ++npred[m]; }
+                last_slot[v] = (int32_t)(f.h_off[m] + j);
             }
         for (int64_t m = M - 1; m >= 0; --m) {
             int32_t h = 0;
-            for (int j = 0; j < 3; ++j) if (succ[m * 3 + j] >= 0) h = std::max(h, height[succ[m * 3 + j]] + 1);
+            for (int j = 0; j < len_of(m); ++j) if (succ[f.h_off[m] + j] >= 0) h = std::max(h, height[succ[f.h_off[m] + j]] + 1);
             height[m] = h;
         }
         using Key = std::pair<int32_t, int32_t>;   // (−height, clause): tallest chain first, then lowest index
@@ -222,8 +259,8 @@ inline std::shared_ptr<TileLevels> build_tile_levels(const odesat_formula& f, in
             while (!ready.empty() && (target <= 0 || (int)take.size() < target)) { take.push_back(ready.top().second); ready.pop(); }
             for (int32_t m : take) level[m] = nlev;
             for (int32_t m : take)
-                for (int j = 0; j < 3; ++j) {
-                    const int32_t q = succ[(size_t)m * 3 + j];
+                for (int j = 0; j < len_of(m); ++j) {
+                    const int32_t q = succ[(size_t)f.h_off[m] + j];
                     if (q >= 0 && --npred[q] == 0) ready.push({-height[q], q});
                 }
             placed += (int64_t)take.size();
@@ -236,24 +273,26 @@ inline std::shared_ptr<TileLevels> build_tile_levels(const odesat_formula& f, in
         std::iota(order.begin(), order.end(), 0);
         std::vector<int32_t> deg(N);
         for (int64_t i = 0; i < N; ++i) deg[i] = f.h_voff[i + 1] - f.h_voff[i];
-        std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
-            const int da = deg[var_of(a, 0)] + deg[var_of(a, 1)] + deg[var_of(a, 2)];
-            const int db = deg[var_of(b, 0)] + deg[var_of(b, 1)] + deg[var_of(b, 2)];
-            return da > db;
-        });
+        std::vector<int64_t> dsum(M, 0);
+        for (int64_t m = 0; m < M; ++m)
+            for (int j = 0; j < len_of(m); ++j) dsum[m] += deg[var_of(m, j)];
+        std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return dsum[a] > dsum[b]; });
         auto colour = [&](int C, int cap, std::vector<int32_t>& lvl) {
             const int words = (C + 63 + 64) / 64;             // slack for overflow colours
             std::vector<uint64_t> bits((size_t)N * words, 0);
             std::vector<int32_t> load((size_t)words * 64, 0);
             int ncol = C;
+            std::vector<uint64_t> forb(words);
             for (int32_t m : order) {
-                const uint64_t* b0 = &bits[(size_t)var_of(m, 0) * words];
-                const uint64_t* b1 = &bits[(size_t)var_of(m, 1) * words];
-                const uint64_t* b2 = &bits[(size_t)var_of(m, 2) * words];
+                const int len = len_of(m);
+                std::fill(forb.begin(), forb.end(), 0);
+                for (int j = 0; j < len; ++j) {
+                    const uint64_t* b = &bits[(size_t)var_of(m, j) * words];
+                    for (int w = 0; w < words; ++w) forb[w] |= b[w];
+                }
                 int best = -1, bl = INT32_MAX;
                 for (int c = 0; c < ncol; ++c) {
-                    const uint64_t forb = b0[c >> 6] | b1[c >> 6] | b2[c >> 6];
-                    if (!((forb >> (c & 63)) & 1) && load[c] < bl && load[c] < cap) { best = c; bl = load[c]; }
+                    if (!((forb[c >> 6] >> (c & 63)) & 1) && load[c] < bl && load[c] < cap) { best = c; bl = load[c]; }
                 }
                 if (best < 0) {
                     if (ncol >= words * 64) throw Error(ODESAT_EINVAL, "balanced schedule ran out of colours");
@@ -261,7 +300,7 @@ inline std::shared_ptr<TileLevels> build_tile_levels(const odesat_formula& f, in
                 }
                 lvl[m] = best;
                 load[best]++;
-                for (int j = 0; j < 3; ++j) bits[(size_t)var_of(m, j) * words + (best >> 6)] |= 1ull << (best & 63);
+                for (int j = 0; j < len; ++j) bits[(size_t)var_of(m, j) * words + (best >> 6)] |= 1ull << (best & 63);
             }
             return ncol;
         };
@@ -337,10 +376,46 @@ inline std::shared_ptr<TileSchedule> build_tile_schedule(const odesat_formula& f
     s->M = f.M;
     double wsum = 0;
     int64_t wcnt = 0;
+    std::vector<int32_t> three, loop;
     for (const auto& b : lv.bucket) {
         if (b.empty()) continue;
         const size_t base0 = s->perm.size();
-        pack_level(f, b, s->perm, s->entry, wsum, wcnt, wide);
+        if (f.K == 3 && f.distinct_vars) pack_level(f, b, s->perm, s->entry, wsum, wcnt, wide);
+        else {
+            // ragged formula: the 3-literal clauses (with three distinct variables) are packed as usual; the others
+            // follow them (so that they share warps) as LOOP clauses whose literals live in `aux`
+            if (wide) throw Error(ODESAT_EUNSUPPORTED, "tile schedule: the cluster kernel needs uniform 3-literal clauses");
+            three.clear();
+            loop.clear();
+            auto plain3 = [&](int32_t m) {   // one to three literals with distinct variables: the packed word
+                const int64_t len = f.h_off[m + 1] - f.h_off[m];
+                if (len < 1 || len > 3) return false;
+                const int32_t* l = &f.h_lits[f.h_off[m]];
+                for (int64_t i = 0; i < len; ++i)
+                    for (int64_t j = i + 1; j < len; ++j)
+                        if (std::abs(l[i]) == std::abs(l[j])) return false;
+                return true;
+            };
+            for (int32_t m : b) (plain3(m) ? three : loop).push_back(m);
+            if (!three.empty()) pack_level(f, three, s->perm, s->entry, wsum, wcnt, wide);
+            for (int32_t m : loop) {
+                const uint32_t len = (uint32_t)(f.h_off[m + 1] - f.h_off[m]);
+                if (len > 0xFFFFu) throw Error(ODESAT_EUNSUPPORTED, "tile schedule: a clause has more than 65535 literals");
+                s->perm.push_back(m);
+                bool distinct = true;
+                for (uint32_t i = 0; i < len && distinct; ++i)
+                    for (uint32_t j = i + 1; j < len && distinct; ++j)
+                        distinct = std::abs(f.h_lits[f.h_off[m] + i]) != std::abs(f.h_lits[f.h_off[m] + j]);
+                s->entry.push_back(pack_entry_loop((uint32_t)s->aux.size(), len, distinct));   // offset: a multiple of 4 words
+                for (uint32_t j = 0; j < len; ++j) {
+                    const int32_t l = f.h_lits[f.h_off[m] + j];
+                    s->aux.push_back(((uint32_t)((l < 0 ? -l : l) - 1) << 4) | (l < 0 ? 0x80000000u : 0u));
+                }
+                if (len == 0) s->aux.push_back(0u);                                    // the kernel reads 16-byte vectors,
+                while (s->aux.size() % 4) s->aux.push_back(0u);                        // the first one unconditionally
+                ++s->n_loop;
+            }
+        }
         const size_t n = s->perm.size() - base0;
         while (s->perm.size() % 8) { s->perm.push_back(-1); s->entry.push_back(0); }   // 128-byte aligned level start
         for (size_t o = 0; o < n; o += (size_t)nt) {
@@ -365,6 +440,8 @@ inline std::shared_ptr<TileSchedule> build_tile_schedule(const odesat_formula& f
     s->d_items2.alloc(std::max<size_t>(s->items2.size(), 1));
     s->d_perm.alloc(std::max<size_t>(s->perm.size(), 1));
     s->d_entry.alloc(std::max<size_t>(s->entry.size(), 1));
+    s->d_aux.alloc(std::max<size_t>(s->aux.size(), 1));
+    if (!s->aux.empty()) ODESAT_CUDA(cudaMemcpy(s->d_aux.p, s->aux.data(), s->aux.size() * 4, cudaMemcpyHostToDevice));
     if (!s->perm.empty()) {
         ODESAT_CUDA(cudaMemcpy(s->d_items.p, s->items.data(), s->items.size() * 4, cudaMemcpyHostToDevice));
         ODESAT_CUDA(cudaMemcpy(s->d_items2.p, s->items2.data(), s->items2.size() * 8, cudaMemcpyHostToDevice));

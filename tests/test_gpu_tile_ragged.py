@@ -1,0 +1,145 @@
+"""Ragged clause lengths in the TILE engine (csrc/tile_ragged.cuh): lengths 0..7, unit and empty clauses (quirk Q9: ±inf
+derivatives), variables repeated inside a clause, uniform k = 4 — bit-identical to the oracle with the EXACT schedule
+and to the GATHER engine, flags and freezing included."""
+import numpy as np
+import pytest
+
+from odesat_b200 import _lib as L
+from odesat_b200 import batch as B
+from odesat_b200 import cnf
+from odesat_b200 import system as S
+from oracle import oracle as O
+
+from helpers import ragged_formula, random_state, repeated_var_formula
+
+pytestmark = pytest.mark.gpu
+
+
+def eq(a, b):
+    return np.array_equal(a, b, equal_nan=True)
+
+
+def both(f):
+    return S.DeviceFormula(f), O.OracleFormula(f.varnum, f.clause_off, f.lits)
+
+
+def mixed_23sat(n_vars, n2, n3, seed):
+    """Binary and ternary clauses with distinct variables (what structured instances mostly consist of)."""
+    rng = np.random.default_rng(seed)
+    off, lits = [0], []
+    for m in range(n2 + n3):
+        k = 2 if m % (n2 + n3) < n2 else 3
+        vs = rng.choice(n_vars, size=k, replace=False) + 1
+        sg = rng.integers(0, 2, size=k) * 2 - 1
+        lits.extend(int(a * b) for a, b in zip(vs, sg))
+        off.append(len(lits))
+    order = rng.permutation(n2 + n3)                          # interleave the two kinds
+    o2, l2 = [0], []
+    for m in order:
+        l2.extend(lits[off[m]:off[m + 1]])
+        o2.append(len(l2))
+    return cnf.Formula(n_vars, np.asarray(o2, np.int64), np.asarray(l2, np.int32), {})
+
+
+FORMULAS = {
+    "ragged": lambda: ragged_formula(3, 300, 1500),           # lengths 0..6, repeats, one empty clause, unused variables
+    "k4": lambda: cnf.random_ksat(400, 5.0, seed=1, k=4),
+    "repeat3": lambda: repeated_var_formula(2, 200, 900),     # uniform 3 with (x, x, y) and (x, -x, y)
+    "mixed23": lambda: mixed_23sat(600, 700, 1500, 4),
+}
+
+
+@pytest.mark.parametrize("prec", [L.F64, L.F32])
+@pytest.mark.parametrize("name", sorted(FORMULAS))
+@pytest.mark.parametrize("R", [1, 33])
+def test_tile_ragged_exact_vs_oracle(prec, name, R):
+    f = FORMULAS[name]()
+    D, F = both(f)
+    dtype = B.np_dtype(prec)
+    b = B.ReplicaBatch(D, R, prec, L.ENGINE_TILE, L.SCHED_EXACT)
+    assert b.engine == L.ENGINE_TILE
+    v, xs, xl = F.init_batch(4, R, dtype)
+    b.upload(v, xs, xl)
+    for n in (1, 70, 59):                                     # 130 steps: crosses the 64-step launch chunk
+        b.run_fixed(0.01, f.default_zeta(), n, freeze=False)
+    F.batch_fixed(v, xs, xl, 0.01, f.default_zeta(), 130, freeze=False, nthreads=4)
+    gv, gxs, gxl = b.download()
+    assert eq(gv, v) and eq(gxs, xs) and eq(gxl, xl)
+
+
+@pytest.mark.parametrize("prec", [L.F64, L.F32])
+def test_tile_ragged_states_outside_the_unit_box_and_large_zeta(prec):
+    """The literal first step (STRICT) and the loop clauses' literal arithmetic with a rigidity term that matters."""
+    f = ragged_formula(5, 120, 500)
+    D, F = both(f)
+    dtype = B.np_dtype(prec)
+    rng = np.random.default_rng(5)
+    R = 16
+    v, xs, xl = random_state(rng, F.N, F.M, dtype, R=R)
+    v[:, ::7] = (rng.uniform(-3, 3, size=v[:, ::7].shape)).astype(dtype)
+    b = B.ReplicaBatch(D, R, prec, L.ENGINE_TILE, L.SCHED_EXACT)
+    g = B.ReplicaBatch(D, R, prec, L.ENGINE_GATHER)
+    for zeta in (0.5, float("inf")):
+        b.upload(v, xs, xl); g.upload(v, xs, xl)
+        b.run_fixed(0.01, zeta, 5, freeze=False); g.run_fixed(0.01, zeta, 5, freeze=False)
+        ov, oxs, oxl = v.copy(), xs.copy(), xl.copy()
+        F.batch_fixed(ov, oxs, oxl, 0.01, zeta, 5, freeze=False)
+        for q in (b, g):
+            gv, gxs, gxl = q.download()
+            assert eq(gv, ov) and eq(gxs, oxs) and eq(gxl, oxl)
+
+
+@pytest.mark.parametrize("prec", [L.F64, L.F32])
+def test_tile_ragged_flags_freezing_and_verification(prec):
+    """An easy mixed 2/3-SAT instance: replicas flag at different steps, take their update (system.rs:149-153) and
+    freeze; flags, states and the exact verification of every replica equal the oracle's / the host evaluation."""
+    f = mixed_23sat(400, 250, 700, 9)
+    D, F = both(f)
+    dtype = B.np_dtype(prec)
+    R = 41
+    b = B.ReplicaBatch(D, R, prec, L.ENGINE_TILE, L.SCHED_EXACT)
+    v, xs, xl = F.init_batch(6, R, dtype)
+    b.upload(v, xs, xl)
+    for n in (300, 500, 700):
+        b.run_fixed(0.01, f.default_zeta(), n, freeze=True)
+    ost = F.batch_fixed(v, xs, xl, 0.01, f.default_zeta(), 1500, freeze=True, nthreads=4)
+    assert (ost >= 0).sum() >= 3
+    gst, _ = b.status()
+    gv, gxs, gxl = b.download()
+    assert eq(gst, ost) and eq(gv, v) and eq(gxs, xs) and eq(gxl, xl)
+    exp = np.array([f.evaluate(v[r] > 0) for r in range(R)], np.uint8)
+    assert eq(b.verify(), exp)
+    assert eq(b.assignment(3), (v[3] > 0).astype(np.uint8))
+
+
+def test_tile_ragged_mid_size_equals_gather_and_balanced_is_close():
+    """N = 6 000 with 30 % binary clauses, f32, 64 replicas, 60 steps: tile (EXACT) == gather bit for bit; BALANCED within
+    rounding."""
+    f = mixed_23sat(6000, 7000, 17000, 12)
+    D = S.DeviceFormula(f)
+    R = 64
+    t = B.ReplicaBatch(D, R, L.F32, L.ENGINE_AUTO, L.SCHED_EXACT)
+    assert t.engine == L.ENGINE_TILE
+    g = B.ReplicaBatch(D, R, L.F32, L.ENGINE_GATHER)
+    c = B.ReplicaBatch(D, R, L.F32, L.ENGINE_TILE, L.SCHED_BALANCED)
+    for q in (t, g, c):
+        q.init(1, 0)
+        q.run_fixed(0.01, f.default_zeta(), 60, freeze=False)
+    tv, txs, txl = t.download()
+    gv, gxs, gxl = g.download()
+    cv, cxs, cxl = c.download()
+    assert eq(tv, gv) and eq(txs, gxs) and eq(txl, gxl)
+    assert np.max(np.abs(cv - gv)) <= 2e-4 and np.max(np.abs(cxs - gxs)) <= 2e-4 and np.max(np.abs(cxl / gxl - 1)) <= 2e-4
+
+
+def test_simulate_batch_on_a_ragged_formula_through_the_c_abi():
+    """One odesat_simulate_batch call (AUTO → tile engine) on the mixed instance: flags and verification as the oracle's."""
+    f = mixed_23sat(400, 250, 700, 9)
+    D, F = both(f)
+    R, steps = 40, 1200
+    v, xs, xl = F.init_batch(6, R, np.float64)
+    res = B.simulate_batch(D, R, v=v.copy(), step_size=0.01, steps=steps, precision=L.F64, mode=L.MODE_BATCH)
+    ost = F.batch_fixed(v, xs, xl, 0.01, f.default_zeta(), steps, freeze=True, nthreads=4)
+    assert eq(res.solved_step, ost)
+    exp = np.array([f.evaluate(v[r] > 0) for r in range(R)], np.uint8)
+    assert eq(res.verified, exp)

@@ -80,12 +80,39 @@ def test_schedule_is_deterministic_and_rejects_unsupported():
     a = compile_schedule(f, L.SCHED_BALANCED, 512, 4)
     b = compile_schedule(f, L.SCHED_BALANCED, 512, 4)
     assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
-    g = cnf.random_ksat(100, 5.0, seed=1, k=4)
+    empty = cnf.Formula(3, np.array([0], np.int64), np.array([], np.int32), {})
     with pytest.raises(L.OdesatError):
-        compile_schedule(g, L.SCHED_EXACT, 512, 4)
-    dup = cnf.Formula(3, np.array([0, 3], np.int64), np.array([1, 1, -2], np.int32), {})
-    with pytest.raises(L.OdesatError):
-        compile_schedule(dup, L.SCHED_EXACT, 128, 2)
+        compile_schedule(empty, L.SCHED_EXACT, 128, 2)
+
+
+@pytest.mark.parametrize("sched", [L.SCHED_EXACT, L.SCHED_BALANCED])
+@pytest.mark.parametrize("which", ["ragged", "k4", "repeat"])
+def test_ragged_schedules_keep_the_level_invariants(sched, which):
+    """Clause lengths other than 3, unit / empty clauses and variables repeated inside a clause compile into LOOP
+    clauses (tile_ragged.cuh): still every clause exactly once, no variable shared by two CLAUSES of a level, and — EXACT —
+    every variable meets its clauses in ascending clause index."""
+    from helpers import ragged_formula, repeated_var_formula
+    f = {"ragged": lambda: ragged_formula(3, 300, 1500), "k4": lambda: cnf.random_ksat(400, 5.0, seed=1, k=4),
+         "repeat": lambda: repeated_var_formula(2, 200, 900)}[which]()
+    nlev, items, perm, wf = compile_schedule(f, sched, 512, 4)
+    assert sorted(perm[perm >= 0]) == list(range(f.n_clauses))
+    assert len(items) % 4 == 0 and len(items) > 4
+    levels = levels_of(items, perm)
+    assert len(levels) == nlev
+    vars_of = [set(int(abs(l)) - 1 for l in f.lits[f.clause_off[m]:f.clause_off[m + 1]]) for m in range(f.n_clauses)]
+    level_of = np.empty(f.n_clauses, np.int64)
+    for li, lv in enumerate(levels):
+        seen = set()
+        for m in lv:
+            assert not (seen & vars_of[m])
+            seen |= vars_of[m]
+        level_of[lv] = li
+    if sched == L.SCHED_EXACT:
+        last = {}
+        for m in range(f.n_clauses):
+            for v in vars_of[m]:
+                assert last.get(v, -1) < level_of[m]
+                last[v] = level_of[m]
 
 
 def test_aim_fixture_schedule(golden_dir):
