@@ -9,8 +9,9 @@
 // once for min / second-min (system.rs:45-58), once for the contributions (system.rs:62-81) — executing the reference's
 // statements literally, so every length (0 and 1 included) yields the reference's bits without any domain argument.
 // Clauses of one to three literals (distinct variables) keep the packed word, the bank-conflict packing and clause_math;
-// a literal position that does not exist enters with the value +inf (system.rs:46-47).  The schedule compiler puts a
-// level's loop clauses behind its 3-literal clauses, so the two kinds mostly sit in different warps, and a level
+// a literal position that does not exist enters with the value +inf (system.rs:46-47).  Under the EXACT schedule clauses
+// of 4..32 distinct literals are GROUP clauses, one lane per literal (clause_group).  The schedule compiler puts a
+// level's group clauses first and its loop clauses last, so the kinds mostly sit in different warps, and a level
 // still never contains two clauses with a common variable (the levels are built from the clauses' real literal lists).
 #pragma once
 
@@ -155,6 +156,80 @@ __device__ __forceinline__ void clause_loop8(unsigned char* smem_raw, const uint
     }
 }
 
+// GROUP clause: four to 32 literals with distinct variables, ONE LANE PER LITERAL (tile_schedule.hpp: P consecutive
+// slots aligned to P inside the warp).  Every lane evaluates its literal (system.rs:49), the group's min / second-min
+// (:50-58 — order statistics of the non-NaN values, duplicates counted, so the fold order does not matter) come from a
+// butterfly of warp shuffles, the leader's {xs, xl} are broadcast, every lane adds its own contribution (:62-81) and the
+// leader updates the memories (:84-95).  Must be called by all 32 lanes of the warp (`grp` false for bystanders).
+// → true for the leader (its cell is to be written back).
+// Used under the EXACT schedule, where every level is one item and waits for its slowest thread: a long clause then
+// costs one literal's latency instead of a chain of them (measurements: tile_schedule.hpp, tile_use_groups).
+template <typename T, int W>
+__device__ __forceinline__ bool clause_group(unsigned char* smem_raw, bool grp, const uint2 e, T (&xs)[W], T (&xl)[W], const bool (&frozen)[W],
+                                             bool (&unsat)[W], T dt, T zeta, T xl_max) {
+    using Row = typename TileTraits<T>::Row;
+    using IO = RowIO<T, W>;
+    const T hi_s = T(1) - Kc<T>::EPSILON;
+    const unsigned lane = threadIdx.x & 31u;
+    const bool live = grp && !(e.y & TILE_ENTRY_VOID);
+    const unsigned P = grp ? (1u << ((e.y >> 8) & 7u)) : 1u;
+    const unsigned pos = grp ? (e.y & 31u) : 0u;
+    Row* const r = reinterpret_cast<Row*>(smem_raw + (live ? (e.x & 0x3FFF0u) : 0u));
+    const T q = (live && (e.x >> 31)) ? T(-1) : T(1);
+    T v[W], d[W], a[W], mn[W], sm[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) { v[w] = T(0); d[w] = T(0); a[w] = inf_v<T>(); mn[w] = inf_v<T>(); sm[w] = inf_v<T>(); }
+    if (live) {
+        IO::unpack(*r, v, d);
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            a[w] = T(1) - q * v[w];                              // :49
+            if (a[w] < mn[w]) mn[w] = a[w];                      // :50-52 on (inf, inf): a NaN never enters
+        }
+    }
+#pragma unroll
+    for (unsigned o = 1; o < 32; o <<= 1) {
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const T ymn = __shfl_xor_sync(0xFFFFFFFFu, mn[w], o), ysm = __shfl_xor_sync(0xFFFFFFFFu, sm[w], o);
+            if (o < P) {                                         // partner inside this lane's group
+                const T lo = rmin(mn[w], ymn), hi = rmax(mn[w], ymn);
+                sm[w] = rmin(hi, rmin(sm[w], ysm));
+                mn[w] = lo;
+            }
+        }
+    }
+    const int src = (int)((lane - pos) & 31u);                   // the group's leader
+    T xsb[W], xlb[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) { xsb[w] = __shfl_sync(0xFFFFFFFFu, xs[w], src); xlb[w] = __shfl_sync(0xFFFFFFFFu, xl[w], src); }
+    if (live) {
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const T cm = T(0.5) * mn[w];                                                    // :60
+            const T wgt = xlb[w] * xsb[w];
+            const T rg = (T(1) + zeta * xlb[w]) * (T(1) - xsb[w]);
+            const T g = (T(0.5) * q) * ((a[w] != mn[w]) ? mn[w] : sm[w]);                  // :64-70
+            const T rr = (cm == a[w]) ? T(0.5) * (q - v[w]) : T(0);                         // :73-77
+            d[w] = d[w] + (wgt * g + rg * rr);                                              // :80
+        }
+        IO::store_dv(r, d);
+    }
+    if (!(live && pos == 0u)) return false;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        const T cm = T(0.5) * mn[w];
+        const T dxs = (Kc<T>::BETA * (xs[w] + Kc<T>::EPSILON)) * (cm - Kc<T>::GAMMA);      // :84
+        const T dxl = Kc<T>::ALPHA * (cm - Kc<T>::DELTA);                                  // :85
+        unsat[w] = unsat[w] || !(cm < Kc<T>::GAMMA);                                       // :88
+        if (!frozen[w]) {
+            xs[w] = euler_clamp(xs[w], dxs, dt, Kc<T>::EPSILON, hi_s);                     // :94
+            xl[w] = euler_clamp(xl[w], dxl, dt, T(1), xl_max);                             // :95
+        }
+    }
+    return true;
+}
+
 // k_tile_fixed<T, NT, D, STRICT, ER = true, QUEUED = false> with loop clauses.  Shared memory as there:
 // rows[N] (16 B) | ring_m[D][NT] (16 B) | ring_e[D][NT] (8 B) | items[n_items].
 template <typename T, int NT, int D, bool STRICT>
@@ -225,11 +300,21 @@ __global__ void __launch_bounds__(NT, 1) k_tile_ragged(const TileArgs<T> a, cons
                 const int i = base + k;
                 const uint2 it = s_items[i];
                 cp_async_wait<D - 1>();                     // this thread's cells of item i have landed
-                if (tid < (it.y & 0x7FFFFFFFu)) {
-                    const Mem mm = my_cell_m[k * NT];
-                    const uint2 e = my_cell_e[k * NT];
-                    T xs[W], xl[W];
-                    IO::unpack_mem(mm, xs, xl);
+                const bool mine = tid < (it.y & 0x7FFFFFFFu);
+                uint2 e = make_uint2(0u, 0u);
+                T xs[W], xl[W];
+#pragma unroll
+                for (int w = 0; w < W; ++w) { xs[w] = T(0); xl[w] = T(0); }
+                if (mine) {
+                    e = my_cell_e[k * NT];
+                    IO::unpack_mem(my_cell_m[k * NT], xs, xl);
+                }
+                const bool grp = mine && (e.y & TILE_ENTRY_GROUP) != 0u;
+                bool write_back = false;
+                if (__any_sync(0xFFFFFFFFu, grp))   // warp-uniform: the whole warp helps with the shuffles
+                    write_back = clause_group<T, W>(smem_raw, grp, e, xs, xl, frozen, unsat, a.dt, a.zeta, a.xl_max);
+                if (mine && !grp) {
+                    write_back = true;
                     if (e.y & TILE_ENTRY_LOOP) {
                         // (bit 26 is a sign bit in a packed entry: TILE_ENTRY_LOOP8 only means something here)
                         if (e.y & TILE_ENTRY_LOOP8)   // four to eight literals, distinct variables (or none at all)
@@ -264,8 +349,8 @@ __global__ void __launch_bounds__(NT, 1) k_tile_ragged(const TileArgs<T> a, cons
                         if (!no1) IO::store_dv(r1, d[1]);
                         if (!no2) IO::store_dv(r2, d[2]);
                     }
-                    __stcg(at16(my_mem, it.x), IO::pack_mem(xs, xl));
                 }
+                if (write_back) __stcg(at16(my_mem, it.x), IO::pack_mem(xs, xl));
                 {   // refill stage k with item i + D (next step's item i + D − n_items at the end)
                     int nx = i + D;
                     if (nx >= n_items) nx -= n_items;

@@ -49,6 +49,7 @@ struct TileSchedule {
     std::vector<int32_t> perm;         // [Mpad] slot → clause index, −1 = padding
     std::vector<uint64_t> entry;       // [Mpad] packed clause: 3×16-bit row + sign bits + valid; or a LOOP clause (below)
     std::vector<uint32_t> aux;         // literal words of the loop clauses: row byte offset | negated << 31, 4-word aligned per clause
+    int64_t n_group = 0;               // group clauses: 4..32 literals, distinct variables, one lane per literal
     int64_t n_loop = 0;                // loop clauses: no literal, more than three, or a repeated variable (tile_ragged.cuh)
     double conflict_wavefronts = 0;    // avg shared-memory wavefronts per quarter-warp access (1 = ideal)
     DevBuf<int32_t> d_perm;
@@ -66,6 +67,17 @@ constexpr uint32_t TILE_ENTRY_LOOP = 1u << 27;
 // flagged (TILE_ENTRY_NO2: no third literal, TILE_ENTRY_NO1: no second one either), their row offset is 0 and the kernel
 // gives them the value +inf, which is what min / second-min start from (system.rs:46-47).
 constexpr uint32_t TILE_ENTRY_NO2 = 1u << 28, TILE_ENTRY_NO1 = 1u << 29;
+// GROUP clauses: four to 32 literals with distinct variables are evaluated by as many LANES of one warp, one literal each
+// (tile_ragged.cuh): the clause occupies P = 4, 8, 16 or 32 consecutive slots aligned to P inside the warp; slot j holds
+// literal j — low word: row byte offset | negated << 31; high word: TILE_ENTRY_GROUP | log2(P) << 8 | j, and
+// TILE_ENTRY_VOID for the slots beyond the clause's length.  Only slot 0 (the leader) owns a {xs, xl} cell
+// (perm = clause index); the others are padding cells (perm = -1).
+constexpr uint32_t TILE_ENTRY_GROUP = 1u << 30, TILE_ENTRY_VOID = 1u << 25;
+inline uint64_t pack_entry_group(uint32_t var, bool neg, uint32_t log2p, uint32_t pos, bool live) {
+    const uint32_t lo = live ? ((var << 4) | (neg ? 0x80000000u : 0u)) : 0u;
+    const uint32_t hi = TILE_ENTRY_GROUP | (log2p << 8) | pos | (live ? 0u : TILE_ENTRY_VOID);
+    return (uint64_t)lo | ((uint64_t)hi << 32);
+}
 // TILE_ENTRY_LOOP8: at most eight literals, all variables distinct — the kernel then takes all rows into registers at once
 constexpr uint32_t TILE_ENTRY_LOOP8 = 1u << 26;
 inline uint64_t pack_entry_loop(uint32_t aux_off, uint32_t len, bool distinct) {
@@ -207,6 +219,28 @@ inline void pack_level(const odesat_formula& f, const std::vector<int32_t>& clau
     }
 }
 
+// Slots a clause occupies in the schedule: 1, or — a GROUP clause (4..32 literals, distinct variables; one lane per
+// literal, tile_ragged.cuh) — its length rounded up to 4 / 8 / 16 / 32.
+// Measured on B200 (N = 10 000, 43 000 clauses of which 2 500 have 5 and 500 have 8 literals, 4 096 replicas, f32, ms per
+// step; gather engine 1.67): EXACT — one 512-slot item per level, every level waits for its slowest thread — 2.57 with
+// the long clauses walked by ONE thread each (clause_loop8: the literal words come from L2, then a chain of eight
+// literals), 1.67 as group clauses; BALANCED — wide levels that absorb slow threads — 1.27 with one thread per clause,
+// 1.68 as groups (a lane per literal costs as many instructions as a whole packed clause: ncu counts 2.5 x the
+// instructions of the uniform kernel).  So: groups under EXACT only.  ODESAT_TILE_GROUPS=0/1 forces them off / on.
+inline bool tile_use_groups(int kind) {
+    const char* e = std::getenv("ODESAT_TILE_GROUPS");   // read per call: the tests switch it between batches
+    return e ? e[0] != '0' : kind == ODESAT_SCHED_EXACT;
+}
+inline int tile_group_log2(const odesat_formula& f, int64_t m, int kind) {   // 0: not a group clause
+    const int64_t len = f.h_off[m + 1] - f.h_off[m];
+    if (!tile_use_groups(kind) || len < 4 || len > 32) return 0;
+    const int32_t* l = &f.h_lits[f.h_off[m]];
+    for (int64_t i = 0; i < len; ++i)
+        for (int64_t j = i + 1; j < len; ++j)
+            if (std::abs(l[i]) == std::abs(l[j])) return 0;
+    return len <= 4 ? 2 : len <= 8 ? 3 : len <= 16 ? 4 : 5;
+}
+
 // Level assignment only (shared by every warp count); cached on the formula.
 struct TileLevels {
     int nlev = 0;
@@ -254,9 +288,20 @@ inline std::shared_ptr<TileLevels> build_tile_levels(const odesat_formula& f, in
         for (int64_t m = 0; m < M; ++m) if (npred[m] == 0) ready.push({-height[m], (int32_t)m});
         std::vector<int32_t> take;
         int64_t placed = 0;
+        // the cap counts SLOTS: a group clause takes one per literal (rounded up), everything else one
+        std::vector<int32_t> weight(M, 1);
+        if (f.K != 3) for (int64_t m = 0; m < M; ++m) { const int lg = tile_group_log2(f, m, kind); if (lg) weight[m] = 1 << lg; }
         while (placed < M) {
             take.clear();
-            while (!ready.empty() && (target <= 0 || (int)take.size() < target)) { take.push_back(ready.top().second); ready.pop(); }
+            int64_t slots = 0;
+            while (!ready.empty() && (target <= 0 || slots < target)) {
+                // (a clause that would overflow the level waits, unless the level is still empty)
+                const int32_t m = ready.top().second;
+                if (target > 0 && slots > 0 && slots + weight[m] > target) break;
+                take.push_back(m);
+                slots += weight[m];
+                ready.pop();
+            }
             for (int32_t m : take) level[m] = nlev;
             for (int32_t m : take)
                 for (int j = 0; j < len_of(m); ++j) {
@@ -277,6 +322,12 @@ inline std::shared_ptr<TileLevels> build_tile_levels(const odesat_formula& f, in
         for (int64_t m = 0; m < M; ++m)
             for (int j = 0; j < len_of(m); ++j) dsum[m] += deg[var_of(m, j)];
         std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return dsum[a] > dsum[b]; });
+        std::vector<int32_t> weight(M, 1);   // slots per clause (group clauses: one per literal, rounded up)
+        int64_t total_slots = M;
+        if (f.K != 3) {
+            total_slots = 0;
+            for (int64_t m = 0; m < M; ++m) { const int lg = tile_group_log2(f, m, kind); if (lg) weight[m] = 1 << lg; total_slots += weight[m]; }
+        }
         auto colour = [&](int C, int cap, std::vector<int32_t>& lvl) {
             const int words = (C + 63 + 64) / 64;             // slack for overflow colours
             std::vector<uint64_t> bits((size_t)N * words, 0);
@@ -299,7 +350,7 @@ inline std::shared_ptr<TileLevels> build_tile_levels(const odesat_formula& f, in
                     best = ncol++;
                 }
                 lvl[m] = best;
-                load[best]++;
+                load[best] += weight[m];
                 for (int j = 0; j < len; ++j) bits[(size_t)var_of(m, j) * words + (best >> 6)] |= 1ull << (best & 63);
             }
             return ncol;
@@ -307,8 +358,9 @@ inline std::shared_ptr<TileLevels> build_tile_levels(const odesat_formula& f, in
         if (ipl == 1) {
             // one item per level: levels of `target` clauses, but never fewer colours than the max variable degree
             // (+ 2 of slack for the greedy); classes are capped at a multiple of `round`
-            const int C = (int)std::max<int64_t>(f.max_degree + 2, (M + target - 1) / target);
-            const int cap = (int)(((M + C - 1) / C + round - 1) / round * round);
+            const int64_t S = total_slots;   // = M for uniform formulas
+            const int C = (int)std::max<int64_t>(f.max_degree + 2, (S + target - 1) / target);
+            const int cap = (int)(((S + C - 1) / C + round - 1) / round * round);
             nlev = colour(C, cap, level);
         } else {
             // WIDE levels (kernels whose ring does not need a barrier after every item): a level is `k` items of
@@ -317,6 +369,7 @@ inline std::shared_ptr<TileLevels> build_tile_levels(const odesat_formula& f, in
             // many items per level as that bound allows.  The greedy has no slack at C·cap ≈ M, so C, C + 1, C + 2
             // are tried and the one with the fewest items (then levels) is kept.
             const int64_t md = std::max<int64_t>(1, f.max_degree);
+            const int64_t M = total_slots;   // (shadows the clause count: the capacities below are in slots)
             // k = 0: the k whose colour count max(md, ceil(M / (k·target))) gives the fewest items (then the fewest levels)
             int64_t k = ipl;
             if (k <= 0) {
@@ -331,11 +384,11 @@ inline std::shared_ptr<TileLevels> build_tile_levels(const odesat_formula& f, in
             const int C0 = (int)std::max<int64_t>(md, (M + k * target - 1) / (k * target));
             int64_t best_items = INT64_MAX;
             int best_lev = 0;
-            std::vector<int32_t> lvl(M, 0);
+            std::vector<int32_t> lvl(f.M, 0);
             for (int C = C0; C <= C0 + 2; ++C) {
                 const int nc = colour(C, (int)(k * target), lvl);
                 std::vector<int32_t> cnt(nc, 0);
-                for (int64_t m = 0; m < M; ++m) cnt[lvl[m]]++;
+                for (int64_t m = 0; m < f.M; ++m) cnt[lvl[m]] += weight[m];
                 int64_t items = 0;
                 int lev = 0;
                 for (int c : cnt) { items += (c + target - 1) / target; lev += c > 0; }
@@ -376,7 +429,7 @@ inline std::shared_ptr<TileSchedule> build_tile_schedule(const odesat_formula& f
     s->M = f.M;
     double wsum = 0;
     int64_t wcnt = 0;
-    std::vector<int32_t> three, loop;
+    std::vector<int32_t> three, loop, group;
     for (const auto& b : lv.bucket) {
         if (b.empty()) continue;
         const size_t base0 = s->perm.size();
@@ -387,6 +440,7 @@ inline std::shared_ptr<TileSchedule> build_tile_schedule(const odesat_formula& f
             if (wide) throw Error(ODESAT_EUNSUPPORTED, "tile schedule: the cluster kernel needs uniform 3-literal clauses");
             three.clear();
             loop.clear();
+            group.clear();
             auto plain3 = [&](int32_t m) {   // one to three literals with distinct variables: the packed word
                 const int64_t len = f.h_off[m + 1] - f.h_off[m];
                 if (len < 1 || len > 3) return false;
@@ -396,7 +450,28 @@ inline std::shared_ptr<TileSchedule> build_tile_schedule(const odesat_formula& f
                         if (std::abs(l[i]) == std::abs(l[j])) return false;
                 return true;
             };
-            for (int32_t m : b) (plain3(m) ? three : loop).push_back(m);
+            for (int32_t m : b) {
+                if (plain3(m)) three.push_back(m);
+                else if (tile_group_log2(f, m, kind)) group.push_back(m);
+                else loop.push_back(m);
+            }
+            // group clauses first, largest first: packed from the level's (8-slot aligned) start, groups of descending
+            // power-of-two size are aligned to their size inside the warps (thread = slot - level start, mod the CTA width)
+            auto log2p_of = [&](int32_t m) { return (uint32_t)tile_group_log2(f, m, kind); };
+            std::stable_sort(group.begin(), group.end(), [&](int32_t x, int32_t y) { return log2p_of(x) > log2p_of(y); });
+            for (int32_t m : group) {
+                const uint32_t len = (uint32_t)(f.h_off[m + 1] - f.h_off[m]), lp = log2p_of(m);
+                for (uint32_t j = 0; j < (1u << lp); ++j) {
+                    s->perm.push_back(j == 0 ? m : -1);
+                    if (j < len) {
+                        const int32_t l = f.h_lits[f.h_off[m] + j];
+                        s->entry.push_back(pack_entry_group((uint32_t)((l < 0 ? -l : l) - 1), l < 0, lp, j, true));
+                    } else s->entry.push_back(pack_entry_group(0, false, lp, j, false));
+                }
+                ++s->n_group;
+            }
+            // holes up to the next octet (pack_level's unit): void non-leader lanes, which do nothing
+            while ((s->perm.size() - base0) % 8) { s->perm.push_back(-1); s->entry.push_back(pack_entry_group(0, false, 0, 1, false)); }
             if (!three.empty()) pack_level(f, three, s->perm, s->entry, wsum, wcnt, wide);
             for (int32_t m : loop) {
                 const uint32_t len = (uint32_t)(f.h_off[m + 1] - f.h_off[m]);

@@ -41,7 +41,22 @@ def mixed_23sat(n_vars, n2, n3, seed):
     return cnf.Formula(n_vars, np.asarray(o2, np.int64), np.asarray(l2, np.int32), {})
 
 
+def long_clause_formula(n_vars, seed):
+    """3-literal clauses mixed with clauses of 4, 7, 9, 17, 33 and 40 distinct literals (group sizes 4 / 8 / 16 / 32 and the
+    serial walk beyond 32)."""
+    rng = np.random.default_rng(seed)
+    off, lits = [0], []
+    for m in range(900):
+        k = int(rng.choice([3, 3, 3, 3, 4, 7, 9, 17, 33, 40]))
+        vs = rng.choice(n_vars, size=k, replace=False) + 1
+        sg = rng.integers(0, 2, size=k) * 2 - 1
+        lits.extend(int(a * b) for a, b in zip(vs, sg))
+        off.append(len(lits))
+    return cnf.Formula(n_vars, np.asarray(off, np.int64), np.asarray(lits, np.int32), {})
+
+
 FORMULAS = {
+    "long": lambda: long_clause_formula(500, 8),
     "ragged": lambda: ragged_formula(3, 300, 1500),           # lengths 0..6, repeats, one empty clause, unused variables
     "k4": lambda: cnf.random_ksat(400, 5.0, seed=1, k=4),
     "repeat3": lambda: repeated_var_formula(2, 200, 900),     # uniform 3 with (x, x, y) and (x, -x, y)
@@ -51,8 +66,11 @@ FORMULAS = {
 
 @pytest.mark.parametrize("prec", [L.F64, L.F32])
 @pytest.mark.parametrize("name", sorted(FORMULAS))
-@pytest.mark.parametrize("R", [1, 33])
-def test_tile_ragged_exact_vs_oracle(prec, name, R):
+@pytest.mark.parametrize("R,groups", [(1, "1"), (33, "1"), (33, "0")])
+def test_tile_ragged_exact_vs_oracle(prec, name, R, groups, monkeypatch):
+    """groups = 1: clauses of 4..32 distinct literals are GROUP clauses (one lane per literal, the EXACT default);
+    groups = 0: one thread walks them (clause_loop8 / clause_loop, the BALANCED default).  Same bits either way."""
+    monkeypatch.setenv("ODESAT_TILE_GROUPS", groups)
     f = FORMULAS[name]()
     D, F = both(f)
     dtype = B.np_dtype(prec)

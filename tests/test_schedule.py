@@ -12,8 +12,8 @@ from odesat_b200 import cnf
 
 def compile_schedule(f, sched, threads, depth):
     out = np.zeros(4, np.int64)
-    perm = np.full(f.n_clauses * 2 + 4096, -7, np.int32)
-    items = np.zeros(f.n_clauses + 4096, np.uint32)
+    perm = np.full(f.n_clauses * 8 + f.n_literals * 2 + 4096, -7, np.int32)   # group clauses take a slot per literal (rounded up to 4 / 8 / 16 / 32)
+    items = np.zeros(f.n_clauses * 2 + 4096, np.uint32)
     P = C.c_void_p
     L.check(L.lib().odesat_tile_schedule_stats(
         f.varnum, f.n_clauses, f.clause_off.ctypes.data_as(P), f.lits.ctypes.data_as(P), sched, threads, depth,
