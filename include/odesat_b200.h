@@ -52,19 +52,24 @@ typedef enum odesat_precision { ODESAT_F64 = 0, ODESAT_F32 = 1 } odesat_precisio
  *          (ascending clause, then literal position) ⇒ bit-identical sums.  Instances whose whole
  *          state fits in the shared memory of one SM (the reference's fixtures) run on a persistent
  *          one-CTA-per-replica kernel with the step loop inside the kernel.
- *  TILE  : throughput path — fixed steps, uniform 3-literal clauses with distinct variables, up to
- *          ≈ 13 000 variables (two f32 replicas / one f64 replica per CTA) or ≈ 27 000 (one f32
- *          replica per CTA): variables of a replica tile resident in shared memory, clauses
- *          streamed in conflict-free levels.  Larger instances can be forced onto a thread-block
- *          cluster (rows in distributed shared memory) by requesting TILE explicitly; AUTO does
- *          not, because the general engine is faster there.
+ *  TILE  : throughput path — up to ≈ 13 000 variables (two f32 replicas / one f64 replica per CTA) or ≈ 27 000
+ *          (one f32 replica per CTA, uniform 3-literal formulas): variables of a replica tile resident in shared
+ *          memory, clauses streamed in conflict-free levels.  Fixed steps on any formula: uniform 3-literal clauses
+ *          with distinct variables run on the packed kernels (tile_engine.cuh, tile_ws.cuh); ragged clause lengths,
+ *          unit / empty clauses and variables repeated inside a clause on k_tile_ragged (tile_ragged.cuh).  Adaptive
+ *          steps (system.rs:111-139, per-replica dt) on uniform 3-literal formulas: k_tile_adaptive
+ *          (tile_adaptive.cuh).  Larger instances can be forced onto a thread-block cluster (rows in distributed
+ *          shared memory) by requesting TILE explicitly; AUTO does not, because the general engine is faster there
+ *          (DESIGN.md §5b).
  *  SLAB  : throughput path for fixed steps on uniform 3-literal formulas that do NOT fit in shared memory (up to
  *          2^20 variables): the gather engine's deterministic two-phase RHS (bit-identical sums) run by ONE
  *          persistent kernel per chunk of steps over slabs of 32 bytes of replicas, ordered so that a slab's
  *          per-literal contributions are consumed while they are still in L2 (csrc/slab_engine.cuh).
  *          Experimental: bit-identical, HBM traffic 13 GB per step against the gather engine's 22.7 GB at N = 50 000,
  *          but latency-bound and slower (4.8 ms against 3.56 ms per step), so AUTO never picks it.
- *  AUTO  : TILE when it applies and the batch has at least 8 replicas, else GATHER. */
+ *  AUTO  : TILE when it applies and the batch has at least 8 replicas, else GATHER.  (Adaptive steps: TILE only where
+ *          it has the adaptive kernel.  Formulas with clauses of more than three literals under the EXACT schedule:
+ *          GATHER, which is as fast there — DESIGN.md §5d.) */
 typedef enum odesat_engine { ODESAT_ENGINE_AUTO = 0, ODESAT_ENGINE_GATHER = 1, ODESAT_ENGINE_TILE = 2, ODESAT_ENGINE_SLAB = 3 } odesat_engine;
 
 /* Clause schedule of the TILE engine.
