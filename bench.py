@@ -482,6 +482,26 @@ def run_gpu(args):
         other = {"schedule": "exact" if osched == L.SCHED_EXACT else "balanced", "ms_per_step": oms_max / args.steps,
                  "value": args.steps * f.n_clauses * total / (oms_max * 1e-3),
                  "roofline_frac": bytes_step * args.steps / (oms * 1e-3) / 1e9 / peak}
+    adapt = None
+    if eng_name == "tile" and not adaptive:
+        # the same shard integrated with ADAPTIVE steps (system.rs:111-139, `batch` without -s) on the tile engine's
+        # adaptive kernel, for the record: one step = two RHS evaluations; bytes = SURVEY §8(d)'s adaptive formula
+        ab = B.ReplicaBatch(F, R, prec, engine, sched)
+        ab.init(RUN_SEED, lo)
+        ab.run_adaptive(1e-3, zeta, args.warmup)
+        barrier()
+        ams = ab.run_adaptive(1e-3, zeta, args.steps, timed=True)
+        barrier()
+        aeng = {L.ENGINE_GATHER: "gather", L.ENGINE_TILE: "tile", L.ENGINE_SLAB: "slab"}[ab.engine]
+        ab.close()
+        t = torch.tensor([ams], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ams_max = float(t.item())
+        abytes = algorithmic_bytes_per_step(f.varnum, f.n_clauses, f.n_literals, R, P, True)
+        adapt = {"engine": aeng, "schedule": args.schedule, "ms_per_adaptive_step": ams_max / args.steps,
+                 "rhs_evals_per_s": 2 * args.steps * f.n_clauses * total / (ams_max * 1e-3),
+                 "roofline_frac_on_adaptive_algorithmic_bytes": abytes * args.steps / (ams * 1e-3) / 1e9 / peak}
     weak = None
     if strong and world > 1 and not adaptive:
         # the weak-scaling figure of the same run: args.replicas replicas on EVERY GPU
@@ -546,7 +566,7 @@ def run_gpu(args):
             "config": make_config(args, f, name, world),
             "detail": {"engine": eng_name, "schedule": args.schedule,
                        "parallelism": f"replica-sharded x{world}, no data-path collective",
-                       "flagged_replicas": flagged, "other_schedule_same_run": other,
+                       "flagged_replicas": flagged, "other_schedule_same_run": other, "adaptive_steps_same_run": adapt,
                        "e2e_call": f"one odesat_simulate_batch call of {e2e_steps} steps per GPU: v0 of every replica "
                                    "from pinned host memory in (uploaded sub-batch by sub-batch, overlapping the integration); "
                                    "per-replica flags, exact verification and the winner's assignment out"},
