@@ -154,3 +154,17 @@ def test_simulate_batch_adaptive_takes_the_tile_engine_and_matches_the_oracle(mo
     assert eq(res.solved_step, ost)
     exp = np.array([f.evaluate(v[r] > 0) for r in range(R)], np.uint8)
     assert eq(res.verified, exp)
+
+
+def test_adaptive_batch_sharded_over_the_devices_of_one_process():
+    """odesat_params::n_gpus with adaptive steps: every shard runs the tile engine's adaptive kernel on its own device;
+    flags and verification equal the single-device call's."""
+    if L.lib().odesat_device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    f = cnf.random_ksat(5000, 2.0, seed=5)                    # M = 10 000: the block-wide kernels (not one warp per tile)
+    D = S.DeviceFormula(f)
+    R, steps = 48, 650
+    one = B.simulate_batch(D, R, seed=4, steps=steps, precision=L.F32, mode=L.MODE_BATCH, n_gpus=1)
+    two = B.simulate_batch(D, R, seed=4, steps=steps, precision=L.F32, mode=L.MODE_BATCH, n_gpus=2)
+    assert eq(one.solved_step, two.solved_step) and eq(one.verified, two.verified) and one.winner == two.winner
+    assert (one.solved_step >= 0).sum() >= 1
