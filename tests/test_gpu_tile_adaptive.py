@@ -168,3 +168,23 @@ def test_adaptive_batch_sharded_over_the_devices_of_one_process():
     two = B.simulate_batch(D, R, seed=4, steps=steps, precision=L.F32, mode=L.MODE_BATCH, n_gpus=2)
     assert eq(one.solved_step, two.solved_step) and eq(one.verified, two.verified) and one.winner == two.winner
     assert (one.solved_step >= 0).sum() >= 1
+
+
+def test_adaptive_tile_kernel_soak_full_batch_equals_gather_engine():
+    """Race evidence in lieu of the closed compute-sanitizer: the FULL bench batch (4 096 replicas of the configs[2] formula,
+    every SM busy, C_m and v_full scratch written and re-read under load), 48 adaptive steps in launches of 1 + 31 + 16,
+    EXACT schedule — bit-identical to the gather engine (which is pinned to the oracle above): states, step sizes, flags."""
+    f = cnf.random_ksat(10_000, 4.3, seed=20240611 + 2)
+    D = S.DeviceFormula(f)
+    R = 4096
+    t = B.ReplicaBatch(D, R, L.F32, L.ENGINE_TILE, L.SCHED_EXACT)
+    g = B.ReplicaBatch(D, R, L.F32, L.ENGINE_GATHER)
+    for q in (t, g):
+        q.init(3, 0)
+        for n in (1, 31, 16):
+            q.run_adaptive(1e-3, f.default_zeta(), n)
+    assert eq(t.dt(), g.dt()) and eq(t.status()[0], g.status()[0])
+    tv, txs, txl = t.download()
+    gv, gxs, gxl = g.download()
+    assert eq(tv, gv) and eq(txs, gxs) and eq(txl, gxl)
+    assert len(np.unique(t.dt())) > 100
