@@ -57,8 +57,8 @@ typedef enum odesat_precision { ODESAT_F64 = 0, ODESAT_F32 = 1 } odesat_precisio
  *          memory, clauses streamed in conflict-free levels.  Fixed steps on any formula: uniform 3-literal clauses
  *          with distinct variables run on the packed kernels (tile_engine.cuh, tile_ws.cuh); ragged clause lengths,
  *          unit / empty clauses and variables repeated inside a clause on k_tile_ragged (tile_ragged.cuh).  Adaptive
- *          steps (system.rs:111-139, per-replica dt) on uniform 3-literal formulas: k_tile_adaptive
- *          (tile_adaptive.cuh).  Larger instances can be forced onto a thread-block cluster (rows in distributed
+ *          steps (system.rs:111-139, per-replica dt): k_tile_adaptive (tile_adaptive.cuh), uniform and ragged formulas
+ *          (except formulas with 4..32-literal clauses under the EXACT schedule).  Larger instances can be forced onto a thread-block cluster (rows in distributed
  *          shared memory) by requesting TILE explicitly; AUTO does not, because the general engine is faster there
  *          (DESIGN.md §5b).
  *  SLAB  : throughput path for fixed steps on uniform 3-literal formulas that do NOT fit in shared memory (up to

@@ -38,6 +38,7 @@ template <typename T> struct TileAdaptArgs {
     T* cm = nullptr;        // [tiles][Mpad][W]  C_m of pass A (scratch)
     T* dt = nullptr;        // [R] per-replica step size, read at launch start, written back at its end
     T tol = T(0);
+    const uint32_t* aux = nullptr;   // literal words of the loop clauses (RAGGED instantiations; tile_schedule.hpp)
 };
 
 // One RHS evaluation of a clause for one replica (system.rs:43-88) without the update: contributions added into d,
@@ -132,8 +133,70 @@ __device__ __forceinline__ void mem_derivs_f32x2(float2 xs, float2 cm, float2& d
     dxl = mul2(bc2(Kc<float>::ALPHA), add2(cm, bc2(-Kc<float>::DELTA)));
 }
 
+// RHS of one LOOP clause (no literal, more than three, or a repeated variable — tile_ragged.cuh) for the W replicas of the
+// tile: system.rs:43-81 statement by statement, contributions added into the dv halves of the rows, → C_m.
+template <typename T, int W>
+__device__ __forceinline__ void clause_loop_rhs(unsigned char* smem_raw, const uint32_t* __restrict__ lits, unsigned len, const T (&xs)[W],
+                                                const T (&xl)[W], T zeta, T (&cm)[W]) {
+    using Row = typename TileTraits<T>::Row;
+    using IO = RowIO<T, W>;
+    T mn[W], sm[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) { mn[w] = inf_v<T>(); sm[w] = inf_v<T>(); }
+    const uint4* lits4 = reinterpret_cast<const uint4*>(lits);
+    for (unsigned j0 = 0; j0 < len; j0 += 4) {
+        const uint4 wa = __ldg(lits4 + (j0 >> 2));
+        const uint32_t lws[4] = {wa.x, wa.y, wa.z, wa.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (j0 + u < len) {
+                const Row* r = reinterpret_cast<const Row*>(smem_raw + (lws[u] & 0x3FFF0u));
+                const T q = (lws[u] >> 31) ? T(-1) : T(1);
+                T v[W], d[W];
+                IO::unpack(*r, v, d);
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                    const T a = T(1) - q * v[w];                                                    // :49
+                    if (a < mn[w]) { sm[w] = mn[w]; mn[w] = a; } else if (a < sm[w]) { sm[w] = a; }   // :50-55
+                }
+            }
+        }
+    }
+    T wgt[W], rg[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        cm[w] = T(0.5) * mn[w];                                                             // :60
+        wgt[w] = xl[w] * xs[w];
+        rg[w] = (T(1) + zeta * xl[w]) * (T(1) - xs[w]);
+    }
+    for (unsigned j0 = 0; j0 < len; j0 += 4) {
+        const uint4 wa = __ldg(lits4 + (j0 >> 2));
+        const uint32_t lws[4] = {wa.x, wa.y, wa.z, wa.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (j0 + u < len) {   // in literal order: a repeated variable sees its own earlier addend
+                Row* r = reinterpret_cast<Row*>(smem_raw + (lws[u] & 0x3FFF0u));
+                const T q = (lws[u] >> 31) ? T(-1) : T(1);
+                T v[W], d[W];
+                IO::unpack(*r, v, d);
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                    const T a = T(1) - q * v[w];
+                    const T g = (T(0.5) * q) * ((a != mn[w]) ? mn[w] : sm[w]);             // :64-70
+                    const T rr = (cm[w] == a) ? T(0.5) * (q - v[w]) : T(0);                 // :73-77
+                    d[w] = d[w] + (wgt[w] * g + rg[w] * rr);                                // :80
+                }
+                IO::store_dv(r, d);
+            }
+        }
+    }
+}
+
+// RAGGED: the schedule may hold one- and two-literal packed clauses (missing positions enter with +inf and are not
+// written) and LOOP clauses; group clauses (EXACT schedules of formulas with 4..32-literal clauses) are not handled here —
+// TileEngine::has_adaptive() is false for those.  RAGGED instantiations use the scalar arithmetic.
 // Shared memory: rows[N] (16 B) | ring_m[D][NT] (16 B) | ring_e[D][NT] (8 B) | ring_c[D][NT] (8 B) | items[n_items]
-template <typename T, int NT, int D, bool STRICT>
+template <typename T, int NT, int D, bool STRICT, bool RAGGED = false>
 __global__ void __launch_bounds__(NT, 1) k_tile_adaptive(const TileAdaptArgs<T> aa) {
     constexpr int W = TileTraits<T>::W;
     using Row = typename TileTraits<T>::Row;
@@ -231,11 +294,22 @@ __global__ void __launch_bounds__(NT, 1) k_tile_adaptive(const TileAdaptArgs<T> 
                         Row* const r2 = reinterpret_cast<Row*>(smem_raw + (e.y & 0x3FFF0u));
                         const T q[3] = {(e.y >> 24) & 1u ? T(-1) : T(1), (e.y >> 25) & 1u ? T(-1) : T(1), (e.y >> 26) & 1u ? T(-1) : T(1)};
                         T v[3][W], d[3][W], xs[W], xl[W];
-                        IO::unpack(*r0, v[0], d[0]);
-                        IO::unpack(*r1, v[1], d[1]);
-                        IO::unpack(*r2, v[2], d[2]);
                         IO::unpack_mem(mm, xs, xl);
-                        if constexpr (!STRICT && W == 2 && sizeof(T) == 4) {
+                        const bool loopc = RAGGED && (e.y & TILE_ENTRY_LOOP) != 0u;
+                        const bool no2 = RAGGED && (e.y & TILE_ENTRY_NO2) != 0u, no1 = RAGGED && (e.y & TILE_ENTRY_NO1) != 0u;
+                        if (!loopc) {
+                            IO::unpack(*r0, v[0], d[0]);
+                            IO::unpack(*r1, v[1], d[1]);
+                            IO::unpack(*r2, v[2], d[2]);
+                            if constexpr (RAGGED) {   // a literal position that does not exist: value +inf (system.rs:46-47)
+#pragma unroll
+                                for (int w = 0; w < W; ++w) {
+                                    if (no2) v[2][w] = -inf_v<T>();
+                                    if (no1) v[1][w] = -inf_v<T>();
+                                }
+                            }
+                        }
+                        if constexpr (!STRICT && W == 2 && sizeof(T) == 4 && !RAGGED) {
                             const float2 v2[3] = {make_float2(v[0][0], v[0][1]), make_float2(v[1][0], v[1][1]), make_float2(v[2][0], v[2][1])};
                             float2 d2[3] = {make_float2(d[0][0], d[0][1]), make_float2(d[1][0], d[1][1]), make_float2(d[2][0], d[2][1])};
                             const float qf[3] = {(float)q[0], (float)q[1], (float)q[2]};
@@ -278,37 +352,46 @@ __global__ void __launch_bounds__(NT, 1) k_tile_adaptive(const TileAdaptArgs<T> 
                             for (int j = 0; j < 3; ++j) { d[j][0] = d2[j].x; d[j][1] = d2[j].y; }
                         } else if (pass == 0) {
                             T cm[W];
+                            if (loopc) clause_loop_rhs<T, W>(smem_raw, aa.aux + e.x, e.y & 0xFFFFu, xs, xl, a.zeta, cm);
 #pragma unroll
                             for (int w = 0; w < W; ++w) {
-                                const T vv[3] = {v[0][w], v[1][w], v[2][w]};
-                                T dd[3] = {d[0][w], d[1][w], d[2][w]};
-                                cm[w] = clause_rhs<T, STRICT>(vv, dd, q, xs[w], xl[w], a.zeta);
-                                d[0][w] = dd[0]; d[1][w] = dd[1]; d[2][w] = dd[2];
+                                if (!loopc) {
+                                    const T vv[3] = {v[0][w], v[1][w], v[2][w]};
+                                    T dd[3] = {d[0][w], d[1][w], d[2][w]};
+                                    cm[w] = clause_rhs<T, STRICT>(vv, dd, q, xs[w], xl[w], a.zeta);
+                                    d[0][w] = dd[0]; d[1][w] = dd[1]; d[2][w] = dd[2];
+                                }
                                 unsat[w] = unsat[w] || !(cm[w] < Kc<T>::GAMMA);                      // :88
                             }
                             // plain store (not .cg): the cp.async.ca of pass B reads it back through this SM's L1
                             *at8(my_cm, it.x) = pack_cm(cm);
                         } else {
-                            T cm1[W];
+                            T cm1[W], xs_f[W], xl_f[W], xs_h[W], xl_h[W], cm2[W];
                             unpack_cm(my_cell_c[k * NT], cm1);
 #pragma unroll
                             for (int w = 0; w < W; ++w) {
                                 const T dxs1 = (Kc<T>::BETA * (xs[w] + Kc<T>::EPSILON)) * (cm1[w] - Kc<T>::GAMMA);   // :84
                                 const T dxl1 = Kc<T>::ALPHA * (cm1[w] - Kc<T>::DELTA);                               // :85
-                                const T xs_f = euler_clamp(xs[w], dxs1, dtw[w], Kc<T>::EPSILON, hi_s);               // :125
-                                const T xl_f = euler_clamp(xl[w], dxl1, dtw[w], T(1), a.xl_max);
-                                const T xs_h = euler_clamp(xs[w], dxs1, hw[w], Kc<T>::EPSILON, hi_s);                // :128
-                                const T xl_h = euler_clamp(xl[w], dxl1, hw[w], T(1), a.xl_max);
-                                const T vv[3] = {v[0][w], v[1][w], v[2][w]};
-                                T dd[3] = {d[0][w], d[1][w], d[2][w]};
-                                const T cm2 = clause_rhs<T, STRICT>(vv, dd, q, xs_h, xl_h, a.zeta);                  // :129
-                                d[0][w] = dd[0]; d[1][w] = dd[1]; d[2][w] = dd[2];
-                                const T dxs2 = (Kc<T>::BETA * (xs_h + Kc<T>::EPSILON)) * (cm2 - Kc<T>::GAMMA);
-                                const T dxl2 = Kc<T>::ALPHA * (cm2 - Kc<T>::DELTA);
-                                const T xs_n = euler_clamp(xs_h, dxs2, hw[w], Kc<T>::EPSILON, hi_s);                 // :130
-                                const T xl_n = euler_clamp(xl_h, dxl2, hw[w], T(1), a.xl_max);
+                                xs_f[w] = euler_clamp(xs[w], dxs1, dtw[w], Kc<T>::EPSILON, hi_s);                    // :125
+                                xl_f[w] = euler_clamp(xl[w], dxl1, dtw[w], T(1), a.xl_max);
+                                xs_h[w] = euler_clamp(xs[w], dxs1, hw[w], Kc<T>::EPSILON, hi_s);                     // :128
+                                xl_h[w] = euler_clamp(xl[w], dxl1, hw[w], T(1), a.xl_max);
+                            }
+                            if (loopc) clause_loop_rhs<T, W>(smem_raw, aa.aux + e.x, e.y & 0xFFFFu, xs_h, xl_h, a.zeta, cm2);   // :129
+#pragma unroll
+                            for (int w = 0; w < W; ++w) {
+                                if (!loopc) {
+                                    const T vv[3] = {v[0][w], v[1][w], v[2][w]};
+                                    T dd[3] = {d[0][w], d[1][w], d[2][w]};
+                                    cm2[w] = clause_rhs<T, STRICT>(vv, dd, q, xs_h[w], xl_h[w], a.zeta);             // :129
+                                    d[0][w] = dd[0]; d[1][w] = dd[1]; d[2][w] = dd[2];
+                                }
+                                const T dxs2 = (Kc<T>::BETA * (xs_h[w] + Kc<T>::EPSILON)) * (cm2[w] - Kc<T>::GAMMA);
+                                const T dxl2 = Kc<T>::ALPHA * (cm2[w] - Kc<T>::DELTA);
+                                const T xs_n = euler_clamp(xs_h[w], dxs2, hw[w], Kc<T>::EPSILON, hi_s);              // :130
+                                const T xl_n = euler_clamp(xl_h[w], dxl2, hw[w], T(1), a.xl_max);
                                 if (!frozen[w]) {
-                                    const T e1 = fabs(xs_f - xs_n), e2 = fabs(xl_f - xl_n);                         // :104-107
+                                    const T e1 = fabs(xs_f[w] - xs_n), e2 = fabs(xl_f[w] - xl_n);                   // :104-107
                                     if (e1 == e1) { const U b = EB::enc(e1); e_loc[w] = b > e_loc[w] ? b : e_loc[w]; }
                                     if (e2 == e2) { const U b = EB::enc(e2); e_loc[w] = b > e_loc[w] ? b : e_loc[w]; }
                                     xs[w] = xs_n;
@@ -317,9 +400,11 @@ __global__ void __launch_bounds__(NT, 1) k_tile_adaptive(const TileAdaptArgs<T> 
                             }
                             __stcg(at16(my_mem, it.x), IO::pack_mem(xs, xl));
                         }
-                        IO::store_dv(r0, d[0]);
-                        IO::store_dv(r1, d[1]);
-                        IO::store_dv(r2, d[2]);
+                        if (!loopc) {   // (a loop clause has written its rows itself)
+                            IO::store_dv(r0, d[0]);
+                            if (!no1) IO::store_dv(r1, d[1]);
+                            if (!no2) IO::store_dv(r2, d[2]);
+                        }
                     }
                     {   // refill stage k with item i + D, wrapping into the other pass (of the next step after pass B)
                         int nx = i + D;
@@ -332,7 +417,7 @@ __global__ void __launch_bounds__(NT, 1) k_tile_adaptive(const TileAdaptArgs<T> 
             }
             if (pass == 0) {
                 // -------------------- flag (:120-122) + variable pass A ---------------------------
-                if constexpr (!STRICT && W == 2 && sizeof(T) == 4) { unsat[0] = !(mx[0] < 0.5f); unsat[1] = !(mx[1] < 0.5f); }
+                if constexpr (!STRICT && W == 2 && sizeof(T) == 4 && !RAGGED) { unsat[0] = !(mx[0] < 0.5f); unsat[1] = !(mx[1] < 0.5f); }
                 unsigned any_unsat = 0;
 #pragma unroll
                 for (int w = 0; w < W; ++w) any_unsat |= (__syncthreads_or((int)unsat[w]) ? 1u : 0u) << w;

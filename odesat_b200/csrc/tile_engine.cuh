@@ -1328,13 +1328,21 @@ template <typename T> struct TileEngine final : TileBase<T> {
     // ring depth of the adaptive kernel (32-byte stages): 3 when the schedule was padded for it and it fits, else 2
     // (the kernel pads the item list to whole rings itself, so any schedule will do; ODESAT_TILE_AD=2/3 overrides)
     int adaptive_depth() const {
-        if (small || ragged) return 0;
+        if (small || (ragged && sched->n_group > 0)) return 0;   // group clauses (EXACT, 4..32 literals): fixed steps only
         static const int env = [] { const char* e = std::getenv("ODESAT_TILE_AD"); return e ? std::atoi(e) : 0; }();
         if (env != 2 && smem_adaptive(f.N, sched->n_items, nt, 3) <= kMaxSmem) return 3;
         return smem_adaptive(f.N, sched->n_items, nt, 2) <= kMaxSmem ? 2 : 0;
     }
     bool has_adaptive() const override { return adaptive_depth() != 0; }
     template <int NT, int D, bool STRICT> void launch_adaptive(const TileAdaptArgs<T>& a) {
+        if constexpr (NT == 128 || NT == 512) {   // the widths of ragged formulas
+            if (ragged) {
+                static uint64_t attr_r = 0;
+                ensure_max_smem(k_tile_adaptive<T, NT, D, STRICT, true>, (int)kMaxSmem, attr_r);
+                k_tile_adaptive<T, NT, D, STRICT, true><<<(unsigned)tiles, NT, smem_adaptive(f.N, sched->n_items, NT, D), stream>>>(a);
+                return;
+            }
+        }
         static uint64_t attr_devs = 0;
         ensure_max_smem(k_tile_adaptive<T, NT, D, STRICT>, (int)kMaxSmem, attr_devs);
         k_tile_adaptive<T, NT, D, STRICT><<<(unsigned)tiles, NT, smem_adaptive(f.N, sched->n_items, NT, D), stream>>>(a);
@@ -1366,7 +1374,7 @@ template <typename T> struct TileEngine final : TileBase<T> {
             a.t.vt = vt.p; a.t.mem = mem.p; a.t.solved = solved;
             a.t.zeta = zeta; a.t.xl_max = T(1e4) * T(f.M);
             a.t.step0 = (int32_t)(step0 + done); a.t.nsteps = (int32_t)k; a.t.freeze = 1;
-            a.vfull = vfull.p; a.cm = cmb.p; a.dt = dt_arr; a.tol = tol;
+            a.vfull = vfull.p; a.cm = cmb.p; a.dt = dt_arr; a.tol = tol; a.aux = sched->d_aux.p;
             if (!zeta_ok || (need_rterm && !oor_valid)) {   // the literal statements (see run_fixed)
                 a.t.nsteps = 1;
                 launch_adaptive_any(a, true, 2);

@@ -188,3 +188,41 @@ def test_ragged_tile_kernel_soak_full_batch_equals_gather_engine(groups, monkeyp
     tv, txs, txl = t.download()
     gv, gxs, gxl = g.download()
     assert eq(tv, gv) and eq(txs, gxs) and eq(txl, gxl)
+
+
+@pytest.mark.parametrize("prec", [L.F64, L.F32])
+@pytest.mark.parametrize("name", sorted(FORMULAS))
+def test_tile_ragged_adaptive_steps_exact_vs_oracle(prec, name, monkeypatch):
+    """Adaptive steps (system.rs:111-139) on ragged formulas in the tile engine (k_tile_adaptive<…, RAGGED>): one- and
+    two-literal packed clauses and loop clauses in both passes; states, per-replica dt and flags equal the oracle's.
+    (Group clauses — the EXACT default for 4..32 literals — have no adaptive form: switched off here.)"""
+    monkeypatch.setenv("ODESAT_TILE_GROUPS", "0")
+    f = FORMULAS[name]()
+    D, F = both(f)
+    dtype = B.np_dtype(prec)
+    R = 33
+    b = B.ReplicaBatch(D, R, prec, L.ENGINE_TILE, L.SCHED_EXACT)
+    assert b.engine == L.ENGINE_TILE
+    v, xs, xl = F.init_batch(4, R, dtype)
+    b.upload(v, xs, xl)
+    for n in (1, 40, 29):
+        b.run_adaptive(1e-3, f.default_zeta(), n)
+    ost, odt = F.batch_adaptive(v, xs, xl, 1e-3, f.default_zeta(), 70, nthreads=4)
+    gv, gxs, gxl = b.download()
+    assert eq(b.status()[0], ost) and eq(b.dt(), odt)
+    assert eq(gv, v) and eq(gxs, xs) and eq(gxl, xl)
+
+
+def test_adaptive_batch_on_ragged_formulas_picks_an_engine_that_can():
+    """AUTO for adaptive steps: 2/3-SAT mixes run on the tile engine's adaptive kernel; a formula whose long clauses are
+    group clauses (EXACT) falls back to the gather engine instead of failing — same results as the oracle either way."""
+    for make, steps in ((lambda: mixed_23sat(6000, 7000, 17000, 12), 12), (lambda: long_clause_formula(500, 8), 30)):
+        f = make()
+        D, F = both(f)
+        R = 24
+        v, xs, xl = F.init_batch(2, R, np.float64)
+        res = B.simulate_batch(D, R, v=v.copy(), steps=steps, precision=L.F64, mode=L.MODE_BATCH, write_back=False)
+        ost, _ = F.batch_adaptive(v, xs, xl, 1e-3, f.default_zeta(), steps, nthreads=4)
+        assert eq(res.solved_step, ost)
+        exp = np.array([f.evaluate(v[r] > 0) for r in range(R)], np.uint8)
+        assert eq(res.verified, exp)
