@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
+#include <functional>
 #include <limits>
 #include <string>
 #include <vector>
@@ -188,8 +189,12 @@ struct DriveResult {
 //
 // `prepare(k)` enqueues shard k's inputs; it is called right before the shard's first chunk, so the host→device
 // copy of shard k + 1 overlaps the integration of shard k.
+// `after_final(k)` (may be empty) is called right after shard k's FINAL chunk has been enqueued (the step budget is then
+// exhausted whatever the flags say): the caller enqueues the shard's result kernels there, so that they run while the
+// other shards still integrate instead of after every shard has drained.
 template <typename Prepare>
-DriveResult drive(std::vector<Shard>& sh, const Resolved& r, int mode, bool lockstep, Prepare&& prepare) {
+DriveResult drive(std::vector<Shard>& sh, const Resolved& r, int mode, bool lockstep, Prepare&& prepare,
+                  const std::function<void(size_t)>& after_final = nullptr) {
     DriveResult out;
     const bool inter = mode == ODESAT_MODE_INTER;
     bool prepared = false;
@@ -228,6 +233,7 @@ DriveResult drive(std::vector<Shard>& sh, const Resolved& r, int mode, bool lock
                 if (r.fixed) s.b->run_fixed_async(r.dt, r.zeta, n, /*freeze=*/1, stop);
                 else s.b->run_adaptive_async(r.tol, r.zeta, n);
                 s.b->post_key(slot, s.off);
+                if (after_final && !lockstep && r.steps >= 0 && issued + n >= r.steps) after_final(k);
             }
             prepared = true;
             issued += n;
@@ -336,6 +342,7 @@ void simulate_batch_impl(const odesat_formula* f, int64_t R, TH* v, TH* xs, TH* 
                             /*reset=*/false);
     };
     std::vector<int64_t> solved((size_t)R, -1);
+    std::vector<char> enqueued(sh.size(), 0);   // shards whose results are already enqueued behind their final chunk
     DriveResult dr;
     if (inter_adaptive) {
         // adaptive inter: the replicas share ONE dt and step one after the other (system.rs:312-349, quirk Q7)
@@ -347,10 +354,16 @@ void simulate_batch_impl(const odesat_formula* f, int64_t R, TH* v, TH* xs, TH* 
         if (dr.key != NO_KEY) dr.run = (dr.key >> 32) + 1;
     } else {
         const bool lockstep = mode == ODESAT_MODE_INTER && write_back != 0 && r.fixed;
-        dr = drive(sh, r, mode, lockstep, prepare);
+        // BATCH: a shard's verification is enqueued behind its final chunk, i.e. it overlaps the other shards' integration
+        // (INTER masks flags after the winning step and may stop mid-budget: its results are taken after the loop)
+        std::function<void(size_t)> early;
+        static const bool early_on = [] { const char* e = std::getenv("ODESAT_EARLY_RESULTS"); return !(e && e[0] == '0'); }();
+        if (mode == ODESAT_MODE_BATCH && early_on) early = [&](size_t k) { sh[k].b->results_enqueue(); enqueued[k] = 1; };
+        dr = drive(sh, r, mode, lockstep, prepare, early);
     }
     std::vector<uint8_t> ver((size_t)R, 0);
-    for (Shard& s : sh) { DeviceGuard g(s.dev); s.b->results_enqueue(); }       // cnf.rs:246-264 on every shard, then
+    for (size_t k = 0; k < sh.size(); ++k)                                       // cnf.rs:246-264 on every shard, then
+        if (!enqueued[k]) { DeviceGuard g(sh[k].dev); sh[k].b->results_enqueue(); }
     for (Shard& s : sh) { DeviceGuard g(s.dev); s.b->results_collect(solved.data() + s.off, ver.data() + s.off); }   // one sync each
     int64_t win = -1, src = 0;
     if (mode == ODESAT_MODE_BATCH) {
