@@ -629,6 +629,7 @@ __global__ void __launch_bounds__(NT, 1) k_tile_fixed_tma(const TileArgs<T> a) {
 #include "tile_ws.cuh"
 #include "tile_adaptive.cuh"
 #include "tile_ragged.cuh"
+#include "tile_adaptive_ws.cuh"
 namespace odesat {
 
 // ---- small-instance persistent kernel ---------------------------------------------
@@ -1352,7 +1353,40 @@ template <typename T> struct TileEngine final : TileBase<T> {
         else if (d == 3) launch_adaptive<NT, 3, false>(a);
         else launch_adaptive<NT, 2, false>(a);
     }
+    // warp-specialised persistent form (tile_adaptive_ws.cuh): f32 BALANCED at the widths of k_tile_ws.  ODESAT_TILE_ADWS=0/1.
+    int adws_env = [] { const char* e = std::getenv("ODESAT_TILE_ADWS"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
+    template <int NT, int D> bool launch_adaptive_ws(const TileAdaptArgs<T>& a) {
+        if constexpr (sizeof(T) == 4) {
+            const size_t smem = (size_t)f.N * 16 + (size_t)NT * D * 32 + (size_t)(sched->n_items + 2) * 8 + (size_t)D * 16 + 16;
+            if (smem > kMaxSmem || !work.p || tiles > (1 << 24)) return false;
+            int real = 0;
+            for (uint32_t it : sched->items) real += ((it >> 20) & 0x7FFu) != 0u;
+            if (real < 2 * D + 2) return false;   // every stage must hold two real items (see k_tile_ws)
+            static uint64_t attr_devs = 0;
+            ensure_max_smem(k_tile_adaptive_ws<NT, D>, (int)kMaxSmem, attr_devs);
+            TileWork wk;
+            wk.counter = work.p;
+            wk.done = work.p + 1;
+            wk.tiles = (int)tiles;
+            wk.ksub = pick_ksub(a.t.nsteps);
+            wk.nsub = (a.t.nsteps + wk.ksub - 1) / wk.ksub;
+            ODESAT_CUDA(cudaMemsetAsync(work.p, 0, ((size_t)tiles + 1) * sizeof(int), stream));
+            const int64_t grid = std::min<int64_t>(tiles * wk.nsub, num_sms);
+            k_tile_adaptive_ws<NT, D><<<(unsigned)grid, NT + 32, smem, stream>>>(a, wk);
+            return true;
+        } else {
+            return false;
+        }
+    }
+    bool try_adaptive_ws(const TileAdaptArgs<T>& a) {
+        const bool want = adws_env >= 0 ? adws_env == 1 : true;
+        if (!want || ragged || sizeof(T) != 4 || sched->kind != ODESAT_SCHED_BALANCED) return false;
+        if (nt == 704) return launch_adaptive_ws<704, 3>(a) || launch_adaptive_ws<704, 2>(a);
+        if (nt == 768) return launch_adaptive_ws<768, 2>(a);
+        return false;
+    }
     void launch_adaptive_any(const TileAdaptArgs<T>& a, bool strict, int d) {
+        if (!strict && try_adaptive_ws(a)) return;
         if (nt == 128) launch_adaptive_nt<128>(a, strict, d);
         else if (nt == 512) launch_adaptive_nt<512>(a, strict, d);
         else if (nt == 640) launch_adaptive_nt<640>(a, strict, d);
@@ -1363,7 +1397,7 @@ template <typename T> struct TileEngine final : TileBase<T> {
     int64_t run_adaptive(T tol, T zeta, int64_t n, int32_t* solved, int64_t step0, T* dt_arr) override {
         const int d = adaptive_depth();
         if (d == 0) throw Error(ODESAT_EUNSUPPORTED, "adaptive steps: the tile kernel's ring does not fit beside this formula's rows (or one-warp tiles); use the gather engine");
-        if (!vfull.p) { vfull.alloc(vt.n, ledger_); cmb.alloc((size_t)(tiles * sched->Mpad * W), ledger_); }
+        if (!vfull.p) { vfull.alloc(vt.n, ledger_); cmb.alloc((size_t)(tiles * sched->Mpad * W) + 8, ledger_); }   // + slack: bulk copies round an item up to 16 bytes
         int64_t launches = 0;
         const bool zeta_ok = std::isfinite((double)zeta);
         for (int64_t done = 0; done < n;) {

@@ -188,3 +188,24 @@ def test_adaptive_tile_kernel_soak_full_batch_equals_gather_engine():
     gv, gxs, gxl = g.download()
     assert eq(tv, gv) and eq(txs, gxs) and eq(txl, gxl)
     assert len(np.unique(t.dt())) > 100
+
+
+@pytest.mark.parametrize("R", [4096, 512, 37])
+def test_warp_specialised_adaptive_kernel_equals_the_per_thread_ring(R, monkeypatch):
+    """k_tile_adaptive_ws (producer warp, bulk copies, C_m through the async proxy, work queue with sub-chunks when the
+    shard has few tiles) against k_tile_adaptive on the SAME BALANCED schedule: identical states, step sizes and flags —
+    race evidence for the ring / proxy-fence protocol at the full batch and on a shard whose tiles hop between SMs."""
+    f = cnf.random_ksat(10_000, 4.3, seed=20240611 + 2)
+    D = S.DeviceFormula(f)
+    out = []
+    for ws in ("1", "0"):
+        monkeypatch.setenv("ODESAT_TILE_ADWS", ws)
+        b = B.ReplicaBatch(D, R, L.F32, L.ENGINE_TILE, L.SCHED_BALANCED)
+        b.init(5, 0)
+        for n in (1, 17, 6):
+            b.run_adaptive(1e-3, f.default_zeta(), n)
+        out.append((b.download(), b.dt(), b.status()[0]))
+        b.close()
+    (s1, d1, f1), (s0, d0, f0) = out
+    assert eq(d1, d0) and eq(f1, f0)
+    assert all(eq(x, y) for x, y in zip(s1, s0))
