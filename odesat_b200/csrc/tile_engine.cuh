@@ -1302,9 +1302,16 @@ template <typename T> struct TileEngine final : TileBase<T> {
         }
     }
     template <int NT, int D, bool STRICT> void launch_ragged(const TileArgs<T>& a) {
-        static uint64_t attr_devs = 0;
-        ensure_max_smem(k_tile_ragged<T, NT, D, STRICT>, (int)kMaxSmem, attr_devs);
-        k_tile_ragged<T, NT, D, STRICT><<<(unsigned)tiles, NT, smem_bytes(f.N, sched->n_items, NT, D), stream>>>(a, sched->d_aux.p);
+        const size_t smem = smem_bytes(f.N, sched->n_items, NT, D);
+        if (sched->n_group > 0) {
+            static uint64_t attr_g = 0;
+            ensure_max_smem(k_tile_ragged<T, NT, D, STRICT, true>, (int)kMaxSmem, attr_g);
+            k_tile_ragged<T, NT, D, STRICT, true><<<(unsigned)tiles, NT, smem, stream>>>(a, sched->d_aux.p);
+        } else {
+            static uint64_t attr_devs = 0;
+            ensure_max_smem(k_tile_ragged<T, NT, D, STRICT, false>, (int)kMaxSmem, attr_devs);
+            k_tile_ragged<T, NT, D, STRICT, false><<<(unsigned)tiles, NT, smem, stream>>>(a, sched->d_aux.p);
+        }
     }
     template <int NT> void launch_ragged_nt(const TileArgs<T>& a, bool strict) {
         if (strict) launch_ragged<NT, 2, true>(a);
