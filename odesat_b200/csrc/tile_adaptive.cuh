@@ -194,7 +194,7 @@ __device__ __forceinline__ void clause_loop_rhs(unsigned char* smem_raw, const u
 
 // RAGGED: the schedule may hold one- and two-literal packed clauses (missing positions enter with +inf and are not
 // written) and LOOP clauses; group clauses (EXACT schedules of formulas with 4..32-literal clauses) are not handled here —
-// TileEngine::has_adaptive() is false for those.  RAGGED instantiations use the scalar arithmetic.
+// TileEngine::has_adaptive() is false for those.
 // Shared memory: rows[N] (16 B) | ring_m[D][NT] (16 B) | ring_e[D][NT] (8 B) | ring_c[D][NT] (8 B) | items[n_items]
 template <typename T, int NT, int D, bool STRICT, bool RAGGED = false>
 __global__ void __launch_bounds__(NT, 1) k_tile_adaptive(const TileAdaptArgs<T> aa) {
@@ -309,48 +309,9 @@ __global__ void __launch_bounds__(NT, 1) k_tile_adaptive(const TileAdaptArgs<T> 
                                 }
                             }
                         }
-                        if constexpr (!STRICT && W == 2 && sizeof(T) == 4 && !RAGGED) {
-                            const float2 v2[3] = {make_float2(v[0][0], v[0][1]), make_float2(v[1][0], v[1][1]), make_float2(v[2][0], v[2][1])};
-                            float2 d2[3] = {make_float2(d[0][0], d[0][1]), make_float2(d[1][0], d[1][1]), make_float2(d[2][0], d[2][1])};
-                            const float qf[3] = {(float)q[0], (float)q[1], (float)q[2]};
-                            const float2 xs2 = make_float2(xs[0], xs[1]), xl2 = make_float2(xl[0], xl[1]);
-                            if (pass == 0) {
-                                const float2 mn = clause_rhs_f32x2(v2, d2, qf, xs2, xl2);
-                                mx[0] = rmax(mx[0], mn.x);              // :88 as a running maximum of the clause minima (packed_f32x2.cuh)
-                                mx[1] = rmax(mx[1], mn.y);
-                                const float2 cm = mul2(bc2(0.5f), mn);                                                   // :60
-                                *at8(my_cm, it.x) = make_uint2(__float_as_uint(cm.x), __float_as_uint(cm.y));
-                            } else {
-                                const uint2 cu = my_cell_c[k * NT];
-                                const float2 cm1 = make_float2(__uint_as_float(cu.x), __uint_as_float(cu.y));
-                                const float2 dt2 = make_float2(dtw[0], dtw[1]), h2 = make_float2(hw[0], hw[1]);
-                                float2 dxs1, dxl1, dxs2, dxl2;
-                                mem_derivs_f32x2(xs2, cm1, dxs1, dxl1);                                                  // :84-85
-                                const float2 xs_f = euler_clamp_f32x2(xs2, dxs1, dt2, Kc<float>::EPSILON, (float)hi_s);  // :125
-                                const float2 xl_f = euler_clamp_f32x2(xl2, dxl1, dt2, 1.0f, (float)a.xl_max);
-                                const float2 xs_h = euler_clamp_f32x2(xs2, dxs1, h2, Kc<float>::EPSILON, (float)hi_s);   // :128
-                                const float2 xl_h = euler_clamp_f32x2(xl2, dxl1, h2, 1.0f, (float)a.xl_max);
-                                const float2 mn = clause_rhs_f32x2(v2, d2, qf, xs_h, xl_h);                              // :129
-                                mem_derivs_f32x2(xs_h, mul2(bc2(0.5f), mn), dxs2, dxl2);
-                                const float2 xs_n = euler_clamp_f32x2(xs_h, dxs2, h2, Kc<float>::EPSILON, (float)hi_s);  // :130
-                                const float2 xl_n = euler_clamp_f32x2(xl_h, dxl2, h2, 1.0f, (float)a.xl_max);
-                                const float es[2] = {fabsf(__fsub_rn(xs_f.x, xs_n.x)), fabsf(__fsub_rn(xs_f.y, xs_n.y))};   // :104-107
-                                const float el[2] = {fabsf(__fsub_rn(xl_f.x, xl_n.x)), fabsf(__fsub_rn(xl_f.y, xl_n.y))};
-                                const float ns[2] = {xs_n.x, xs_n.y}, nl[2] = {xl_n.x, xl_n.y};
-#pragma unroll
-                                for (int w = 0; w < W; ++w) {
-                                    if (!frozen[w]) {
-                                        if (es[w] == es[w]) { const U b = (U)EB::enc((T)es[w]); e_loc[w] = b > e_loc[w] ? b : e_loc[w]; }
-                                        if (el[w] == el[w]) { const U b = (U)EB::enc((T)el[w]); e_loc[w] = b > e_loc[w] ? b : e_loc[w]; }
-                                        xs[w] = (T)ns[w];
-                                        xl[w] = (T)nl[w];
-                                    }
-                                }
-                                __stcg(at16(my_mem, it.x), IO::pack_mem(xs, xl));
-                            }
-#pragma unroll
-                            for (int j = 0; j < 3; ++j) { d[j][0] = d2[j].x; d[j][1] = d2[j].y; }
-                        } else if (pass == 0) {
+                        constexpr bool PACKED = !STRICT && W == 2 && sizeof(T) == 4;   // packed f32x2 arithmetic (not for loop clauses)
+                        auto scalar_clause = [&]() {
+                        if (pass == 0) {
                             T cm[W];
                             if (loopc) clause_loop_rhs<T, W>(smem_raw, aa.aux + e.x, e.y & 0xFFFFu, xs, xl, a.zeta, cm);
 #pragma unroll
@@ -400,6 +361,51 @@ __global__ void __launch_bounds__(NT, 1) k_tile_adaptive(const TileAdaptArgs<T> 
                             }
                             __stcg(at16(my_mem, it.x), IO::pack_mem(xs, xl));
                         }
+                        };
+                        if constexpr (!PACKED) scalar_clause();
+                        else if (loopc) scalar_clause();
+                        else {
+                            const float2 v2[3] = {make_float2(v[0][0], v[0][1]), make_float2(v[1][0], v[1][1]), make_float2(v[2][0], v[2][1])};
+                            float2 d2[3] = {make_float2(d[0][0], d[0][1]), make_float2(d[1][0], d[1][1]), make_float2(d[2][0], d[2][1])};
+                            const float qf[3] = {(float)q[0], (float)q[1], (float)q[2]};
+                            const float2 xs2 = make_float2(xs[0], xs[1]), xl2 = make_float2(xl[0], xl[1]);
+                            if (pass == 0) {
+                                const float2 mn = clause_rhs_f32x2(v2, d2, qf, xs2, xl2);
+                                mx[0] = rmax(mx[0], mn.x);              // :88 as a running maximum of the clause minima (packed_f32x2.cuh)
+                                mx[1] = rmax(mx[1], mn.y);
+                                const float2 cm = mul2(bc2(0.5f), mn);                                                   // :60
+                                *at8(my_cm, it.x) = make_uint2(__float_as_uint(cm.x), __float_as_uint(cm.y));
+                            } else {
+                                const uint2 cu = my_cell_c[k * NT];
+                                const float2 cm1 = make_float2(__uint_as_float(cu.x), __uint_as_float(cu.y));
+                                const float2 dt2 = make_float2(dtw[0], dtw[1]), h2 = make_float2(hw[0], hw[1]);
+                                float2 dxs1, dxl1, dxs2, dxl2;
+                                mem_derivs_f32x2(xs2, cm1, dxs1, dxl1);                                                  // :84-85
+                                const float2 xs_f = euler_clamp_f32x2(xs2, dxs1, dt2, Kc<float>::EPSILON, (float)hi_s);  // :125
+                                const float2 xl_f = euler_clamp_f32x2(xl2, dxl1, dt2, 1.0f, (float)a.xl_max);
+                                const float2 xs_h = euler_clamp_f32x2(xs2, dxs1, h2, Kc<float>::EPSILON, (float)hi_s);   // :128
+                                const float2 xl_h = euler_clamp_f32x2(xl2, dxl1, h2, 1.0f, (float)a.xl_max);
+                                const float2 mn = clause_rhs_f32x2(v2, d2, qf, xs_h, xl_h);                              // :129
+                                mem_derivs_f32x2(xs_h, mul2(bc2(0.5f), mn), dxs2, dxl2);
+                                const float2 xs_n = euler_clamp_f32x2(xs_h, dxs2, h2, Kc<float>::EPSILON, (float)hi_s);  // :130
+                                const float2 xl_n = euler_clamp_f32x2(xl_h, dxl2, h2, 1.0f, (float)a.xl_max);
+                                const float es[2] = {fabsf(__fsub_rn(xs_f.x, xs_n.x)), fabsf(__fsub_rn(xs_f.y, xs_n.y))};   // :104-107
+                                const float el[2] = {fabsf(__fsub_rn(xl_f.x, xl_n.x)), fabsf(__fsub_rn(xl_f.y, xl_n.y))};
+                                const float ns[2] = {xs_n.x, xs_n.y}, nl[2] = {xl_n.x, xl_n.y};
+#pragma unroll
+                                for (int w = 0; w < W; ++w) {
+                                    if (!frozen[w]) {
+                                        if (es[w] == es[w]) { const U b = (U)EB::enc((T)es[w]); e_loc[w] = b > e_loc[w] ? b : e_loc[w]; }
+                                        if (el[w] == el[w]) { const U b = (U)EB::enc((T)el[w]); e_loc[w] = b > e_loc[w] ? b : e_loc[w]; }
+                                        xs[w] = (T)ns[w];
+                                        xl[w] = (T)nl[w];
+                                    }
+                                }
+                                __stcg(at16(my_mem, it.x), IO::pack_mem(xs, xl));
+                            }
+#pragma unroll
+                            for (int j = 0; j < 3; ++j) { d[j][0] = d2[j].x; d[j][1] = d2[j].y; }
+                        }
                         if (!loopc) {   // (a loop clause has written its rows itself)
                             IO::store_dv(r0, d[0]);
                             if (!no1) IO::store_dv(r1, d[1]);
@@ -417,7 +423,7 @@ __global__ void __launch_bounds__(NT, 1) k_tile_adaptive(const TileAdaptArgs<T> 
             }
             if (pass == 0) {
                 // -------------------- flag (:120-122) + variable pass A ---------------------------
-                if constexpr (!STRICT && W == 2 && sizeof(T) == 4 && !RAGGED) { unsat[0] = !(mx[0] < 0.5f); unsat[1] = !(mx[1] < 0.5f); }
+                if constexpr (!STRICT && W == 2 && sizeof(T) == 4) { unsat[0] = unsat[0] || !(mx[0] < 0.5f); unsat[1] = unsat[1] || !(mx[1] < 0.5f); }
                 unsigned any_unsat = 0;
 #pragma unroll
                 for (int w = 0; w < W; ++w) any_unsat |= (__syncthreads_or((int)unsat[w]) ? 1u : 0u) << w;
