@@ -126,6 +126,10 @@ template <typename T> struct BatchImpl final : BatchBase {
     DevBuf<int32_t> solved_snap;
     int64_t step_snap = 0;
     bool v_in_range_snap = false;
+    // the formula as this batch's kernels see it: the formula's own device view, or — single large instances on the gather
+    // engine — its sorted view (formula.hpp): clause rows stored by smallest variable, xs / xl rows permuted on the way in / out
+    FormulaDev fd;
+    const int32_t* cperm = nullptr;   // storage position → original clause (sorted view), device
     // ---- tile engine state ----
     std::unique_ptr<TileBase<T>> tile;   // TileEngine (one CTA per tile) or ClusterTileEngine (one cluster per replica)
 
@@ -194,6 +198,16 @@ template <typename T> struct BatchImpl final : BatchBase {
             if (need_adaptive && tile && !tile->has_adaptive()) { tile.reset(); engine = ODESAT_ENGINE_GATHER; }
         }
         if (engine == ODESAT_ENGINE_SLAB) tile.reset(new SlabEngine<T>(*f, R, stream, &dev_bytes));
+        fd = f->dev;
+        {   // Measured on B200 (N = 1 M, alpha = 4.2, R = 1, adaptive): see DESIGN §4.  ODESAT_GATHER_SORT=0/1 overrides.
+            const char* e = std::getenv("ODESAT_GATHER_SORT");
+            const bool want = e ? e[0] != '0' : (f->N >= 100000);
+            if (!tile && R == 1 && want && f->M > 0 && !small_ok(true)) {
+                const auto& sv = f->sorted_view();
+                fd = sv.dev;
+                cperm = sv.cperm.p;
+            }
+        }
         if (!tile) {
             S[0].alloc(N, M, Rp, &dev_bytes);   // S[1] (derivatives / adaptive ping-pong) on first use
             pick_slab();
@@ -234,8 +248,15 @@ template <typename T> struct BatchImpl final : BatchBase {
     }
 
     // host [R][X] → device [X][Rp]
-    void put(const void* host, T* dst, int64_t X) {
+    void put(const void* host, T* dst, int64_t X, bool clause_rows = false) {
         if (X == 0 || R == 0) return;
+        if (R == 1 && clause_rows && cperm) {   // sorted view: dst[p] = host[cperm[p]]
+            ensure_staging();
+            ODESAT_CUDA(cudaMemcpyAsync(staging.p, host, (size_t)X * sizeof(T), cudaMemcpyHostToDevice, stream));
+            k_permute_rows<T><<<(unsigned)((X + 255) / 256), 256, 0, stream>>>(staging.p, dst, cperm, X, /*gather=*/1);
+            ++launches;
+            return;
+        }
         if (R == 1) {
             ODESAT_CUDA(cudaMemcpyAsync(dst, host, (size_t)X * sizeof(T), cudaMemcpyHostToDevice, stream));
             return;
@@ -246,8 +267,16 @@ template <typename T> struct BatchImpl final : BatchBase {
         k_transpose_in<T><<<g, b, 0, stream>>>(staging.p, dst, R, X, Rp);
         ++launches;
     }
-    void get(void* host, const T* src, int64_t X) {
+    void get(void* host, const T* src, int64_t X, bool clause_rows = false) {
         if (X == 0 || R == 0) return;
+        if (R == 1 && clause_rows && cperm) {   // sorted view: host[cperm[p]] = src[p]
+            ensure_staging();
+            k_permute_rows<T><<<(unsigned)((X + 255) / 256), 256, 0, stream>>>(src, staging.p, cperm, X, /*gather=*/0);
+            ++launches;
+            ODESAT_CUDA(cudaMemcpyAsync(host, staging.p, (size_t)X * sizeof(T), cudaMemcpyDeviceToHost, stream));
+            ODESAT_CUDA(cudaStreamSynchronize(stream));   // staging is reused by the next get()
+            return;
+        }
         if (R == 1) {
             ODESAT_CUDA(cudaMemcpyAsync(host, src, (size_t)X * sizeof(T), cudaMemcpyDeviceToHost, stream));
             return;
@@ -290,11 +319,11 @@ template <typename T> struct BatchImpl final : BatchBase {
         if (tile && tile->has_direct() && gen_xs && gen_xl && !canon_ahead && R > 0) {
             // memories straight into the tile layout; v (if generated) through the canonical scratch and a v-only
             // import — no full-state layout conversion.  When !gen_v the tile keeps its v (or upload(v) follows).
-            launches += tile->init_mem(f->dev.xs0);
+            launches += tile->init_mem(fd.xs0);
             if (gen_v && f->N > 0) {
                 dim3 g, b;
                 geom(f->N, g, b);
-                k_init_state<T><<<g, b, 0, stream>>>(s.v.p, s.xs.p, s.xl.p, f->dev.xs0, f->N, f->M, R, Rp, seed, replica_offset, 1, 0, 0);
+                k_init_state<T><<<g, b, 0, stream>>>(s.v.p, s.xs.p, s.xl.p, fd.xs0, f->N, f->M, R, Rp, seed, replica_offset, 1, 0, 0);
                 ++launches;
                 launches += tile->import_v(s.v.p, Rp);
             }
@@ -308,7 +337,7 @@ template <typename T> struct BatchImpl final : BatchBase {
         dim3 g, b;
         geom(f->N + f->M, g, b);
         if (f->N + f->M > 0 && R > 0) {
-            k_init_state<T><<<g, b, 0, stream>>>(s.v.p, s.xs.p, s.xl.p, f->dev.xs0, f->N, f->M, R, Rp, seed,
+            k_init_state<T><<<g, b, 0, stream>>>(s.v.p, s.xs.p, s.xl.p, fd.xs0, f->N, f->M, R, Rp, seed,
                                                   replica_offset, gen_v, gen_xs, gen_xl);
             ++launches;
         }
@@ -330,8 +359,8 @@ template <typename T> struct BatchImpl final : BatchBase {
         }
         if (tile && !(v && xs && xl)) tile_to_canon();
         if (v) put(v, s.v.p, f->N);
-        if (xs) put(xs, s.xs.p, f->M);
-        if (xl) put(xl, s.xl.p, f->M);
+        if (xs) put(xs, s.xs.p, f->M, true);
+        if (xl) put(xl, s.xl.p, f->M, true);
         ODESAT_CUDA(cudaGetLastError());
         canon_to_tile();
         if (!tile) check_range();
@@ -341,8 +370,8 @@ template <typename T> struct BatchImpl final : BatchBase {
         tile_to_canon();
         StateBuf<T>& s = canon();
         if (v) get(v, s.v.p, f->N);
-        if (xs) get(xs, s.xs.p, f->M);
-        if (xl) get(xl, s.xl.p, f->M);
+        if (xs) get(xs, s.xs.p, f->M, true);
+        if (xl) get(xl, s.xl.p, f->M, true);
         ODESAT_CUDA(cudaGetLastError());
         ODESAT_CUDA(cudaStreamSynchronize(stream));
     }
@@ -388,7 +417,7 @@ template <typename T> struct BatchImpl final : BatchBase {
 
     GatherArgs<T> base_args(double zeta, bool slabbed = false) {
         GatherArgs<T> a;
-        a.f = f->dev;
+        a.f = fd;
         a.R = R;
         a.Rp = Rp;
         a.rep0 = 0;
@@ -472,7 +501,7 @@ template <typename T> struct BatchImpl final : BatchBase {
     void run_small(bool adaptive, double dt, double tol, double zeta, int64_t n, int freeze, const unsigned long long* stop_key) {
         SmallArgs<T> a;
         a.stop_key = stop_key;
-        a.f = f->dev;
+        a.f = fd;
         a.R = R; a.Rp = Rp;
         a.v = S[cur].v.p; a.xs = S[cur].xs.p; a.xl = S[cur].xl.p;
         a.dt_arr = dtv.p;
@@ -639,7 +668,7 @@ template <typename T> struct BatchImpl final : BatchBase {
         // dtv[0] is the shared dt on the small path; the general path keeps it in a separate slot
         if (small_ok(true)) {
             SmallArgs<T> a;
-            a.f = f->dev;
+            a.f = fd;
             a.R = R; a.Rp = Rp;
             a.v = S[cur].v.p; a.xs = S[cur].xs.p; a.xl = S[cur].xl.p;
             a.dt_arr = dtv.p;
@@ -754,7 +783,7 @@ template <typename T> struct BatchImpl final : BatchBase {
         if (f->M > 0 && !done) {
             dim3 g, b;
             geom(f->M, g, b);
-            k_verify<T><<<g, b, 0, stream>>>(f->dev, s.v.p, R, Rp, bad_buf.p);
+            k_verify<T><<<g, b, 0, stream>>>(fd, s.v.p, R, Rp, bad_buf.p);
             ++launches;
         }
         ODESAT_CUDA(cudaGetLastError());
@@ -791,7 +820,7 @@ template <typename T> struct BatchImpl final : BatchBase {
         if (f->M > 0 && !done) {
             dim3 g, b;
             geom(f->M, g, b);
-            k_verify<T><<<g, b, 0, stream>>>(f->dev, s.v.p, R, Rp, bad.p);
+            k_verify<T><<<g, b, 0, stream>>>(fd, s.v.p, R, Rp, bad.p);
             ++launches;
         }
         std::vector<uint32_t> h((size_t)R);
@@ -842,8 +871,8 @@ template <typename T> struct BatchImpl final : BatchBase {
         a.ov = S[1 - cur].v.p; a.oxs = S[1 - cur].xs.p; a.oxl = S[1 - cur].xl.p;
         launch_gather<G_DERIV>(a);
         if (dv) get(dv, S[1 - cur].v.p, f->N);
-        if (dxs) get(dxs, S[1 - cur].xs.p, f->M);
-        if (dxl) get(dxl, S[1 - cur].xl.p, f->M);
+        if (dxs) get(dxs, S[1 - cur].xs.p, f->M, true);
+        if (dxl) get(dxl, S[1 - cur].xl.p, f->M, true);
         std::vector<uint32_t> h((size_t)std::max<int64_t>(R, 1), 0);
         ODESAT_CUDA(cudaMemcpyAsync(h.data(), unsat.p, (size_t)R * 4, cudaMemcpyDeviceToHost, stream));
         ODESAT_CUDA(cudaStreamSynchronize(stream));
@@ -857,8 +886,8 @@ template <typename T> struct BatchImpl final : BatchBase {
         ensure_alt();
         StateBuf<T>& d = S[1 - cur];
         put(dv, d.v.p, f->N);
-        put(dxs, d.xs.p, f->M);
-        put(dxl, d.xl.p, f->M);
+        put(dxs, d.xs.p, f->M, true);
+        put(dxl, d.xl.p, f->M, true);
         if (f->N + f->M > 0 && R > 0) {
             dim3 g, b;
             geom(f->N + f->M, g, b);
@@ -875,8 +904,8 @@ template <typename T> struct BatchImpl final : BatchBase {
         ensure_alt();
         StateBuf<T>& d = S[1 - cur];
         put(bv, d.v.p, f->N);
-        put(bxs, d.xs.p, f->M);
-        put(bxl, d.xl.p, f->M);
+        put(bxs, d.xs.p, f->M, true);
+        put(bxl, d.xl.p, f->M, true);
         ODESAT_CUDA(cudaMemsetAsync(err.p, 0, err.bytes(), stream));
         if (f->N + f->M > 0) {
             dim3 g, b;

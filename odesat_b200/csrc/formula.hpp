@@ -5,6 +5,9 @@
 // its occurrences sorted by (clause, literal position) — the order in which the reference's
 // sequential clause loop adds into dy.v[i] (system.rs:35-80).
 #pragma once
+#include <algorithm>
+#include <climits>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <string>
@@ -45,6 +48,58 @@ struct odesat_formula {
     // Declared after `peers`: the batches are destroyed before the formulas they point to.
     mutable std::vector<std::shared_ptr<void>> batch_cache;
     mutable std::string cache_key;
+
+    // SORTED VIEW (large single instances on the gather engine): the same formula with its clauses STORED in the order of
+    // their smallest variable, so that neighbouring clause rows gather neighbouring v rows (one of the three random L2
+    // sectors per clause becomes a streamed one) and their first contributions land next to each other.  The
+    // variable→clause lists keep the ORIGINAL (clause, position) order — the reference's summation order — and only
+    // point into the permuted storage.  cperm[p] = original index of the clause stored at p (xs / xl rows are permuted
+    // on upload and download).  Built on first use, on the formula's own device.
+    struct SortedView {
+        odesat::DevBuf<int32_t> coff, lits, occ_clause, occ_slot, cperm;
+        odesat::DevBuf<int8_t> xs0;
+        odesat::FormulaDev dev;
+    };
+    mutable std::unique_ptr<SortedView> sorted;
+    const SortedView& sorted_view() const {
+        using namespace odesat;
+        if (sorted) return *sorted;
+        std::unique_ptr<SortedView> v(new SortedView);
+        std::vector<int32_t> order(M), key(M), pos(M);
+        for (int64_t m = 0; m < M; ++m) {
+            int32_t k = INT32_MAX;
+            for (int64_t j = h_off[m]; j < h_off[m + 1]; ++j) k = std::min(k, std::abs(h_lits[j]));
+            key[m] = k;
+            order[m] = (int32_t)m;
+        }
+        std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
+        std::vector<int32_t> coff(M + 1, 0), lits(L), occ_c(L), occ_s(L);
+        std::vector<int8_t> xs0(M);
+        for (int64_t p = 0; p < M; ++p) {
+            const int32_t m = order[p];
+            pos[m] = (int32_t)p;
+            const int64_t len = h_off[m + 1] - h_off[m];
+            for (int64_t j = 0; j < len; ++j) lits[coff[p] + j] = h_lits[h_off[m] + j];
+            coff[p + 1] = coff[p] + (int32_t)len;
+            xs0[p] = h_xs0[m];
+        }
+        for (int64_t e = 0; e < L; ++e) {
+            const int32_t m = h_occ_clause[e];
+            occ_c[e] = pos[m];
+            occ_s[e] = coff[pos[m]] + (int32_t)(h_occ_slot[e] - h_off[m]);
+        }
+        auto up = [](auto& buf, const auto& host) {
+            buf.alloc(host.size());
+            if (!host.empty())
+                ODESAT_CUDA(cudaMemcpy(buf.p, host.data(), host.size() * sizeof(host[0]), cudaMemcpyHostToDevice));
+        };
+        up(v->coff, coff); up(v->lits, lits); up(v->occ_clause, occ_c); up(v->occ_slot, occ_s); up(v->cperm, order); up(v->xs0, xs0);
+        v->dev = dev;
+        v->dev.coff = v->coff.p; v->dev.lits = v->lits.p; v->dev.occ_clause = v->occ_clause.p; v->dev.occ_slot = v->occ_slot.p;
+        v->dev.xs0 = v->xs0.p;
+        sorted = std::move(v);
+        return *sorted;
+    }
 
     // this formula on CUDA device `dev_id` (the handle itself on its own device)
     const odesat_formula* on_device(int dev_id) const {

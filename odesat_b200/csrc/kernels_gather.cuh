@@ -777,6 +777,16 @@ template <typename T> __global__ void k_fill(T* p, int64_t n, T x) {
 }
 
 // Host layout [R][X] (one vector per replica, the reference's Vec<State>) ↔ replica-major [X][Rp].
+// rows of a single instance between the caller's clause order and the sorted view's storage order (formula.hpp):
+// gather: dst[p] = src[perm[p]];  scatter: dst[perm[p]] = src[p]
+template <typename T>
+__global__ void k_permute_rows(const T* __restrict__ src, T* __restrict__ dst, const int32_t* __restrict__ perm, int64_t X, int gather) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= X) return;
+    if (gather) dst[p] = src[perm[p]];
+    else dst[perm[p]] = src[p];
+}
+
 template <typename T>
 __global__ void k_transpose_in(const T* __restrict__ src, T* __restrict__ dst, int64_t R, int64_t X, int64_t Rp) {
     __shared__ T tile[32][33];

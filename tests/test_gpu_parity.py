@@ -75,6 +75,24 @@ def test_rhs_update_and_steps_bit_exact(golden_dir, name, dtype):
         assert eq(s2.v, o[0]) and eq(s2.xs, o[1]) and eq(s2.xl, o[2])
 
 
+@pytest.mark.parametrize("name", ["rand3", "ragged", "repeat3"])
+def test_sorted_clause_view_of_single_instances_is_invisible(golden_dir, name, monkeypatch):
+    """Large single instances run on a view of the formula whose clauses are STORED by smallest variable (formula.hpp,
+    -12 % at N = 1 M); the variable→clause lists keep the reference's summation order and xs / xl rows are permuted on the
+    way in and out.  Forced on here for small formulas: RHS, update, error norm, fixed and adaptive steps and `simulate`
+    must return the caller's clause order and the oracle's bits."""
+    monkeypatch.setenv("ODESAT_GATHER_SORT", "1")
+    monkeypatch.setenv("ODESAT_SMALL", "0")                  # the block-wide gather kernels, not the one-CTA small-instance kernel
+    test_rhs_update_and_steps_bit_exact(golden_dir, name, np.float64)
+    f = FORMULAS[name](golden_dir)
+    D, F = both(f)
+    v, xs, xl = F.init_batch(3, 1)
+    st = S.State(v[0].copy(), xs[0].copy(), xl[0].copy())
+    S.simulate(st, D, None, None, 60, None)                  # 60 adaptive steps (system.rs:156-239)
+    ost, odt = F.batch_adaptive(v, xs, xl, 1e-3, f.default_zeta(), 60)
+    assert eq(st.v, v[0]) and eq(st.xs, xs[0]) and eq(st.xl, xl[0])
+
+
 def test_kat_satisfied_state_flags(golden_dir):
     f = cnf.load_dimacs(str(golden_dir / "toy_mixed.cnf"))
     D, _ = both(f)
