@@ -130,6 +130,13 @@ template <typename T> struct BatchImpl final : BatchBase {
     // engine — its sorted view (formula.hpp): clause rows stored by smallest variable, xs / xl rows permuted on the way in / out
     FormulaDev fd;
     const int32_t* cperm = nullptr;   // storage position → original clause (sorted view), device
+    // replica batches on the gather engine: measured on B200 at N = 50 000 x 2 048 replicas (configs[4]'s share), f32:
+    // 3.568 -> 3.474 ms/step with the sorted view (one of the three v rows of a clause is then shared with its neighbours
+    // in L2); default from N = 30 000 (smaller formulas run on the tile engine).  ODESAT_GATHER_SORT_BATCH_N overrides.
+    static int64_t sort_min_n_batch() {
+        const char* e = std::getenv("ODESAT_GATHER_SORT_BATCH_N");
+        return e ? std::atoll(e) : 30000;
+    }
     // ---- tile engine state ----
     std::unique_ptr<TileBase<T>> tile;   // TileEngine (one CTA per tile) or ClusterTileEngine (one cluster per replica)
 
@@ -201,8 +208,8 @@ template <typename T> struct BatchImpl final : BatchBase {
         fd = f->dev;
         {   // Measured on B200 (N = 1 M, alpha = 4.2, R = 1, adaptive): see DESIGN §4.  ODESAT_GATHER_SORT=0/1 overrides.
             const char* e = std::getenv("ODESAT_GATHER_SORT");
-            const bool want = e ? e[0] != '0' : (f->N >= 100000);
-            if (!tile && R == 1 && want && f->M > 0 && !small_ok(true)) {
+            const bool want = e ? e[0] != '0' : (R == 1 ? f->N >= 100000 : f->N >= sort_min_n_batch());
+            if (!tile && R >= 1 && want && f->M > 0 && !small_ok(true) && !small_ok(false)) {
                 const auto& sv = f->sorted_view();
                 fd = sv.dev;
                 cperm = sv.cperm.p;
@@ -264,7 +271,7 @@ template <typename T> struct BatchImpl final : BatchBase {
         ensure_staging();
         ODESAT_CUDA(cudaMemcpyAsync(staging.p, host, (size_t)(R * X) * sizeof(T), cudaMemcpyHostToDevice, stream));
         dim3 g((unsigned)((X + 31) / 32), (unsigned)((R + 31) / 32)), b(32, 8);
-        k_transpose_in<T><<<g, b, 0, stream>>>(staging.p, dst, R, X, Rp);
+        k_transpose_in<T><<<g, b, 0, stream>>>(staging.p, dst, R, X, Rp, clause_rows ? cperm : nullptr);
         ++launches;
     }
     void get(void* host, const T* src, int64_t X, bool clause_rows = false) {
@@ -283,7 +290,7 @@ template <typename T> struct BatchImpl final : BatchBase {
         }
         ensure_staging();
         dim3 g((unsigned)((X + 31) / 32), (unsigned)((R + 31) / 32)), b(32, 8);
-        k_transpose_out<T><<<g, b, 0, stream>>>(src, staging.p, R, X, Rp);
+        k_transpose_out<T><<<g, b, 0, stream>>>(src, staging.p, R, X, Rp, clause_rows ? cperm : nullptr);
         ++launches;
         ODESAT_CUDA(cudaMemcpyAsync(host, staging.p, (size_t)(R * X) * sizeof(T), cudaMemcpyDeviceToHost, stream));
         ODESAT_CUDA(cudaStreamSynchronize(stream));   // staging is reused by the next get()

@@ -788,12 +788,14 @@ __global__ void k_permute_rows(const T* __restrict__ src, T* __restrict__ dst, c
 }
 
 template <typename T>
-__global__ void k_transpose_in(const T* __restrict__ src, T* __restrict__ dst, int64_t R, int64_t X, int64_t Rp) {
+// perm (may be NULL): device row x holds the caller's row perm[x] (sorted clause view, formula.hpp)
+__global__ void k_transpose_in(const T* __restrict__ src, T* __restrict__ dst, int64_t R, int64_t X, int64_t Rp,
+                               const int32_t* __restrict__ perm) {
     __shared__ T tile[32][33];
     const int64_t x0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
     for (int k = threadIdx.y; k < 32; k += blockDim.y) {
         const int64_t r = r0 + k, x = x0 + threadIdx.x;
-        if (r < R && x < X) tile[k][threadIdx.x] = src[r * X + x];
+        if (r < R && x < X) tile[k][threadIdx.x] = src[r * X + (perm ? (int64_t)perm[x] : x)];
     }
     __syncthreads();
     for (int k = threadIdx.y; k < 32; k += blockDim.y) {
@@ -802,7 +804,8 @@ __global__ void k_transpose_in(const T* __restrict__ src, T* __restrict__ dst, i
     }
 }
 template <typename T>
-__global__ void k_transpose_out(const T* __restrict__ src, T* __restrict__ dst, int64_t R, int64_t X, int64_t Rp) {
+__global__ void k_transpose_out(const T* __restrict__ src, T* __restrict__ dst, int64_t R, int64_t X, int64_t Rp,
+                                const int32_t* __restrict__ perm) {
     __shared__ T tile[32][33];
     const int64_t x0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
     for (int k = threadIdx.y; k < 32; k += blockDim.y) {
@@ -812,7 +815,7 @@ __global__ void k_transpose_out(const T* __restrict__ src, T* __restrict__ dst, 
     __syncthreads();
     for (int k = threadIdx.y; k < 32; k += blockDim.y) {
         const int64_t r = r0 + k, x = x0 + threadIdx.x;
-        if (r < R && x < X) dst[r * X + x] = tile[threadIdx.x][k];
+        if (r < R && x < X) dst[r * X + (perm ? (int64_t)perm[x] : x)] = tile[threadIdx.x][k];
     }
 }
 
